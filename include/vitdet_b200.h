@@ -1,0 +1,196 @@
+/*
+ * vitdet_b200.h — C ABI of the B200-native ViT-detector forward + anchor-free head decode.
+ *
+ * This is the drop-in boundary for ONE path of westlake-moonlight/vision_transformer_detector:
+ *     create_vision_transformer_detector(...)   vision_transformer_detector.py:498-583
+ *     model.predict(images) / model(images)     forward graph built by :239-495
+ *     transform_predictions(logits)             :586-647
+ *     0.5 / 0.5 score thresholding              :2257-2283 (visualise copy), :1359-1384 (metric copy)
+ *
+ * The reference has no FFI of its own (it is pure Python on Keras/TF 2.9); the entry points below
+ * are what a ctypes binding of that path needs — see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VITDET_E_* code; nothing throws across the
+ *     ABI; vitdet_last_error() returns a thread-local, human-readable description of the last failure;
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *     default stream); all device work is asynchronous on that stream unless stated otherwise;
+ *   - the caller owns every buffer it passes in; the library owns only its packed weights, its
+ *     workspace and (for the *_host calls) its pinned staging buffers;
+ *   - one handle per (device, stream); a handle is not thread-safe;
+ *   - there is NO CPU fallback: creating a handle without an sm_100 device fails with
+ *     VITDET_E_NO_DEVICE.
+ */
+#ifndef VITDET_B200_H_
+#define VITDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITDET_ABI_VERSION 1
+
+enum {
+    VITDET_OK = 0,
+    VITDET_E_INVALID = -1,      /* bad argument / unsupported configuration */
+    VITDET_E_NO_DEVICE = -2,    /* no CUDA device of compute capability 10.x */
+    VITDET_E_CUDA = -3,         /* a CUDA runtime / driver call failed */
+    VITDET_E_NOT_FOUND = -4,    /* unknown weight name */
+    VITDET_E_SHAPE = -5,        /* weight shape mismatch */
+    VITDET_E_UNSET = -6         /* forward called before every weight was set */
+};
+
+/* Arithmetic mode of the forward pass.
+ *   BF16: bf16 operands on the tcgen05 tensor cores, f32 accumulation, f32 residual stream,
+ *         LayerNorm / softmax statistics in f32  (tolerance vs the f64 oracle: 2e-2).
+ *   FP32: every product and sum in IEEE f32, as the reference computes (tolerance 1e-3). */
+enum { VITDET_MODE_BF16 = 0, VITDET_MODE_FP32 = 1 };
+
+/* Keyword arguments of create_vision_transformer_detector (det.py:498-506) plus the module
+ * constants of det.py:19-43 that parameterise the head and the decode. */
+typedef struct vitdet_config {
+    int32_t image_h, image_w;          /* input_shape[0], input_shape[1]; default Constants.MODEL_IMAGE_SIZE = 608, 608 */
+    int32_t patch_size;                /* default 17 */
+    int32_t embedding_dim;             /* default 28 */
+    int32_t num_heads;                 /* encoder_num_heads, default 8 */
+    int32_t key_dim;                   /* encoder_key_dim, default 40 (<= 64 in this build) */
+    int32_t mlp_quantities;            /* encoder_mlp_quantities, default 8 */
+    int32_t repeat_times;              /* encoder_repeat_times, default 8 */
+    int32_t head_last_units;           /* mlp_head_last_units, default 136 */
+    int32_t head_dense_layers;         /* mlp_head_dense_layers_quantity, default 7 */
+    int32_t head_block_repeats;        /* mlp_head_dense_mish_block_repeats, default 1 */
+    int32_t use_mish;                  /* 1: Mish, 0: tanh-GELU (tfa.layers.GELU default) */
+    int32_t num_slots;                 /* Constants.MAX_DETECT_OBJECTS_QUANTITY = 17 */
+    int32_t classes;                   /* Constants.CLASSES = 80 */
+    float ln_epsilon;                  /* keras LayerNormalization default 1e-3 */
+} vitdet_config;
+
+typedef struct vitdet_handle vitdet_handle;
+
+int vitdet_abi_version(void);
+const char* vitdet_last_error(void);
+
+/* Fills *cfg with the reference defaults (det.py:498-506, :19-43). */
+void vitdet_default_config(vitdet_config* cfg);
+
+/* Replaces create_vision_transformer_detector(...) (det.py:498-583): validates the configuration,
+ * allocates the packed weight storage on the current CUDA device.  Weights start unset. */
+int vitdet_create(const vitdet_config* cfg, vitdet_handle** out);
+void vitdet_destroy(vitdet_handle* h);
+
+/* Derived shape facts (det.py:274, :285): tokens per image, patch vector length, parameters. */
+int vitdet_tokens(const vitdet_handle* h);
+int vitdet_patch_dim(const vitdet_handle* h);
+int64_t vitdet_count_params(const vitdet_handle* h);
+
+/* Weight exchange — the surface keras `model.weights` / `get_weights()` / `set_weights()` expose
+ * (used by the reference at det.py:2123-2125, :2155-2157).  Weights are enumerated in Keras'
+ * `model.weights` order and named by Keras variable name without the ':0' suffix
+ * (e.g. "multi_head_attention_3/query/kernel"); shapes are the Keras shapes. */
+int vitdet_num_weights(const vitdet_handle* h);
+int vitdet_weight_info(const vitdet_handle* h, int index, char* name, int name_capacity, int* ndim,
+                       int64_t shape[4]);
+/* `data` is HOST float32 in Keras layout (Dense kernel = (in, units); MHA kernels (D,H,d)/(H,d,D));
+ * synchronous. */
+int vitdet_set_weight(vitdet_handle* h, const char* name, const float* data, int ndim, const int64_t* shape);
+int vitdet_get_weight(const vitdet_handle* h, const char* name, float* data, int64_t capacity);
+
+/* Encoder micro-batch: images pushed through the encoder per pass (bounds the workspace; the head
+ * always runs over the whole batch).  Default 64. */
+int vitdet_set_chunk(vitdet_handle* h, int images_per_chunk);
+/* Bytes of device workspace a forward of batch B in `mode` uses. */
+size_t vitdet_workspace_bytes(const vitdet_handle* h, int B, int mode);
+
+/* Measurement hooks (no reference counterpart; bench.py's live roofline uses them).
+ * profile_enable: bit c of the mask turns on CUDA-event timing (on the launching stream) around every
+ * launch of kernel category c; profile_read synchronises the pending events and returns the accumulated
+ * device time and launch count of one category; launch_count = kernels launched by forward calls. */
+int vitdet_profile_enable(vitdet_handle* h, uint32_t category_mask);
+int vitdet_profile_num_categories(const vitdet_handle* h);
+const char* vitdet_profile_category_name(int category);
+int vitdet_profile_read(vitdet_handle* h, int category, double* total_ms, int64_t* launches, int reset);
+int64_t vitdet_launch_count(vitdet_handle* h, int reset);
+
+/* Replaces model.predict(x) / model(x, training=False):
+ * images_dev: DEVICE float32 NHWC [B, image_h, image_w, 3]; logits_dev: DEVICE float32 [B, num_slots, 6]
+ * raw logits (the output of 'MLP_Head_no_Sigmoid', det.py:489-493). */
+int vitdet_forward(vitdet_handle* h, const float* images_dev, int B, float* logits_dev, int mode, void* stream);
+
+/* Decode parameters: thresholds (Constants.OBJECTNESS_THRESHOLD / CLASSIFICATION_CONFIDENCE_THRESHOLD),
+ * comparison rule and the image size transform_predictions scales by (det.py:637-640). */
+typedef struct vitdet_decode_params {
+    float objectness_threshold;        /* default 0.5 */
+    float classification_threshold;    /* default 0.5 */
+    int32_t strict;                    /* 1: keep iff score >  thr (metric rule, det.py:1381-1384)
+                                          0: keep iff score >= thr (visualise rule, det.py:2264, :2282) */
+    float image_h, image_w;            /* Constants.MODEL_IMAGE_SIZE */
+    int32_t classes;                   /* Constants.CLASSES */
+    int32_t use_transform_predictions; /* 1 (default): inputs are raw logits, apply transform_predictions first;
+                                          0: inputs are already decoded rows (the `use_transform_predictions=False`
+                                          path of MeanAveragePrecision.update_state, det.py:1340-1341) */
+} vitdet_decode_params;
+
+/* Output record arrays of the decode, all DEVICE pointers, any of them may be NULL:
+ *   decoded   [R,6] f32  transform_predictions output: conf, class in [0,classes-1], cx, cy, h, w (pixels)
+ *   class_id  [R]   i32  round-half-even(class)                              (det.py:1366, :2271)
+ *   class_conf[R]   f32  (0.5 - |class - id|) / 0.5                           (det.py:1376, :2279)
+ *   keep      [R]   u8   1 iff both scores pass their thresholds
+ *   corners   [R,4] i32  x0,y0,x1,y1: int() truncation then clip to the image (det.py:2300-2325) */
+typedef struct vitdet_detections {
+    float* decoded;
+    int32_t* class_id;
+    float* class_conf;
+    uint8_t* keep;
+    int32_t* corners;
+} vitdet_detections;
+
+/* Replaces transform_predictions (det.py:586-647) + the threshold rule on R = B*num_slots rows of
+ * DEVICE logits.  Stateless: needs no handle. */
+int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* params,
+                  const vitdet_detections* out, void* stream);
+
+/* Same on HOST buffers (what a numpy caller of transform_predictions needs): logits_host [R,6] f32,
+ * every non-NULL member of out_host is a HOST array; copies in, decodes on the GPU, copies back,
+ * synchronises. */
+int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_params* params,
+                       const vitdet_detections* out_host);
+
+/* Forward with the decode fused into the head's last Dense (one launch fewer, logits never re-read).
+ * logits_dev may be NULL. */
+int vitdet_forward_decode(vitdet_handle* h, const float* images_dev, int B, int mode,
+                          const vitdet_decode_params* params, float* logits_dev,
+                          const vitdet_detections* out, void* stream);
+
+/* The reference-facing call with HOST buffers (what model.predict + transform_predictions +
+ * thresholding do for a numpy caller): copies `images_host` to the device through pinned staging,
+ * runs forward+decode, copies the requested outputs back and synchronises.  All pointers are HOST
+ * pointers; any output may be NULL. */
+int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int mode,
+                        const vitdet_decode_params* params, float* logits_host,
+                        const vitdet_detections* out_host, void* stream);
+
+/* ---- operator-level entry points (the Keras layers the path is built from; used by the parity
+ * tests to check each kernel against the oracle in isolation).  All pointers are DEVICE pointers. ---- */
+
+/* keras.layers.Dense (+ activation + residual): out[M,N] = act(A[M,K] @ kernel[K,N] + bias) + resid.
+ * A, kernel (Keras layout), bias, resid, out are float32; mode selects the tensor-core (operands
+ * rounded to bf16) or the f32 CUDA-core kernel.  act: 0 none, 1 Mish, 2 tanh-GELU.  Synchronous. */
+int vitdet_op_dense(const float* A, const float* kernel, const float* bias, const float* resid, float* out,
+                    int M, int K, int N, int act, int mode, void* stream);
+/* keras.layers.LayerNormalization(axis=-1): x, y [M,D] f32. */
+int vitdet_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D,
+                        float eps, void* stream);
+/* Core of keras.layers.MultiHeadAttention after the q/k/v projections:
+ * q,k,v,out: [B,T,H,d] f32 (q already includes its bias, NOT yet scaled by 1/sqrt(d)). Synchronous. */
+int vitdet_op_attention(const float* q, const float* k, const float* v, float* out, int B, int T, int H,
+                        int d, int mode, void* stream);
+/* tf.image.extract_patches(SAME) + Reshape: images [B,H,W,3] f32 -> patches [B*T, 3*p*p] f32. */
+int vitdet_op_patchify(const float* images, int B, int H, int W, int p, float* patches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITDET_B200_H_ */

@@ -1,0 +1,180 @@
+"""GPU parity tests, whole path: create -> set_weights -> predict -> decode, through the reference-facing
+Python API (which calls the C ABI), against the float64 oracle on identical weights and images."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from _util import TOL_BF16, TOL_FP32, build_model, images, oracle, rel_err, tiny_config
+import vision_transformer_detector_b200 as vd
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "threshold_vectors.json")
+
+
+def test_library_weight_table_matches_host_table():
+    for cfg in (vd.DetectorConfig(), tiny_config(mlp_head_dense_mish_block_repeats=2)):
+        m = vd.VisionTransformerDetector(cfg, seed=None)
+        assert m._specs == vd.weight_specs(cfg)
+        assert m.count_params() == sum(int(np.prod(s)) for _, s in vd.weight_specs(cfg))
+        m.close()
+
+
+def test_create_defaults_and_api_surface():
+    m = vd.create_vision_transformer_detector()
+    assert m.name == "vision_transformer_detector"
+    assert m.input_shape == (None, 608, 608, 3) and m.output_shape == (None, 17, 6)
+    assert len(m.weights) == 245 and m.weights[0].name == "linear_projection/kernel:0"
+    assert m.count_params() == 131_476_891
+    w = m.get_weights()
+    assert len(w) == 245 and w[0].shape == (867, 28)
+    m2 = vd.VisionTransformerDetector.from_config(m.get_config(), seed=None)
+    m2.set_weights(w)                                            # det.py:2123-2125, :2155-2157 usage
+    assert all(np.array_equal(a, b) for a, b in zip(m2.get_weights(), w))
+    with pytest.raises(ValueError):
+        m2.set_weights(w[:-1])
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((1, 600, 608, 3), np.float32))
+    x = images(m.config, 1)
+    assert m.predict(x).shape == (1, 17, 6)
+    m.close(); m2.close()
+
+
+def test_unset_weights_fail_loudly():
+    m = vd.VisionTransformerDetector(tiny_config(), seed=None)
+    with pytest.raises(vd._capi.VitdetError) as ei:
+        m.predict(images(m.config, 1))
+    assert ei.value.code == vd._capi.E_UNSET
+    m.close()
+
+
+@pytest.mark.parametrize("use_mish", [True, False])
+@pytest.mark.parametrize("mode,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_tiny_model_logits_match_oracle(mode, tol, use_mish):
+    cfg = tiny_config(use_mish=use_mish)
+    w = vd.random_weights(cfg, seed=11, spread=True)
+    x = images(cfg, 5)
+    ref = oracle.forward(w, cfg, x, np.float64)
+    m = build_model(cfg, w, mode)
+    got = m.predict(x)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < tol
+    m.close()
+
+
+@pytest.mark.parametrize("cfg_over", [
+    dict(input_shape=(64, 64, 3), patch_size=16, embedding_dim=64, encoder_num_heads=4, encoder_key_dim=64,
+         encoder_mlp_quantities=3, encoder_repeat_times=2),                       # ViT-B-like proportions, no padding
+    dict(input_shape=(136, 68, 3), encoder_num_heads=3, encoder_key_dim=24, mlp_head_dense_mish_block_repeats=2),
+    dict(encoder_mlp_quantities=1, encoder_repeat_times=1, mlp_head_dense_layers_quantity=1),
+])
+def test_configuration_knobs(cfg_over):
+    cfg = tiny_config(**cfg_over)
+    w = vd.random_weights(cfg, seed=4, spread=True)
+    x = images(cfg, 3)
+    ref = oracle.forward(w, cfg, x, np.float64)
+    for mode, tol in (("fp32", TOL_FP32), ("bf16", TOL_BF16)):
+        m = build_model(cfg, w, mode)
+        assert rel_err(m.predict(x), ref) < tol
+        m.close()
+
+
+def _exact_decode_check(logits_gpu, rec, ref_logits, image_size):
+    """north_star: in the fp32 mode, decoded detection indices and classes must be bit-exact wherever
+    the reference's scores are not within tolerance of a threshold (bands 0.25*|dl| on
+    sigma_0 and 39.5*|dl| on the class confidence, plus the rounding boundary of the class id)."""
+    ref = oracle.decode(ref_logits, image_size=image_size)
+    dl = float(np.abs(np.asarray(logits_gpu, np.float64) - ref_logits).max())
+    obj, cc = ref["decoded"][..., 0], ref["class_conf"]
+    near = (np.abs(obj - 0.5) <= 0.25 * dl + 1e-6) | (np.abs(cc - 0.5) <= 39.5 * dl + 1e-5) | (cc <= 39.5 * dl + 1e-5)
+    keep = np.asarray(rec.keep).astype(bool)
+    assert np.array_equal(keep[~near], ref["keep"][~near])
+    assert np.array_equal(np.asarray(rec.class_id)[~near], ref["class_id"][~near])
+    return int((~near).sum()), int(ref["keep"].sum())
+
+
+def test_default_model_fp32_logits_and_exact_detections():
+    """configs[0]-style case on the GPU: default config, Keras-default init AND the spread set."""
+    cfg = vd.DetectorConfig()
+    x = images(cfg, 2)
+    for seed, spread in ((0, False), (1, True)):
+        w = vd.random_weights(cfg, seed=seed, spread=spread)
+        ref = oracle.forward(w, cfg, x, np.float64)
+        m = build_model(cfg, w, "fp32")
+        rec = m.detect(x, image_size=(608, 608))
+        assert rel_err(rec.logits, ref) < TOL_FP32
+        checked, kept = _exact_decode_check(rec.logits, rec, ref, (608, 608))
+        assert checked >= 17                                    # the exactness check must not be vacuous
+        # transform_predictions itself, on the GPU's own logits: float32 arithmetic vs float64
+        dec_ref = oracle.transform_predictions(np.asarray(rec.logits, np.float64))
+        assert np.abs(np.asarray(rec.decoded) - dec_ref).max() < 608 * 1e-6
+        m.close()
+
+
+def test_default_model_bf16_logits():
+    cfg = vd.DetectorConfig()
+    x = images(cfg, 3)
+    w = vd.random_weights(cfg, seed=1, spread=True)
+    ref = oracle.forward(w, cfg, x, np.float64)
+    m = build_model(cfg, w, "bf16")
+    got = m.predict(x)
+    assert rel_err(got, ref) < TOL_BF16
+    # images are independent: chunked execution gives the same rows
+    m.set_chunk(2)
+    assert np.array_equal(m.predict(x), got)
+    m.close()
+
+
+def test_device_tensor_path_equals_host_path():
+    import torch
+    cfg = tiny_config()
+    w = vd.random_weights(cfg, seed=2, spread=True)
+    x = images(cfg, 4)
+    m = build_model(cfg, w, "bf16")
+    host = m.predict(x)
+    dev = m(torch.from_numpy(x).cuda(), training=False)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+    rec_h = m.detect(x)
+    rec_d = m.detect(torch.from_numpy(x).cuda())
+    for a, b in zip((rec_h.decoded, rec_h.class_id, rec_h.class_conf, rec_h.keep, rec_h.corners),
+                    (rec_d.decoded, rec_d.class_id, rec_d.class_conf, rec_d.keep, rec_d.corners)):
+        assert np.array_equal(a, b.cpu().numpy())
+    m.close()
+
+
+def test_decode_reproduces_reference_golden_vectors():
+    g = json.load(open(GOLDEN))
+    slots = np.array([r["slot"] for r in g["reference"]], np.float32)
+    rec = vd.decode_predictions(slots, strict=True, use_transform_predictions=False)
+    assert rec.keep.astype(bool).tolist() == [r["keep_strict"] for r in g["reference"]]
+    assert rec.class_id.tolist() == [r["class_id"] for r in g["reference"]]
+    assert np.array_equal(rec.decoded, slots)
+    d = np.array([r["slot"] for r in g["derived"]], np.float32)
+    rs = vd.decode_predictions(d, strict=True, use_transform_predictions=False)
+    rv = vd.decode_predictions(d, strict=False, use_transform_predictions=False)
+    assert rs.keep.astype(bool).tolist() == [r["keep_strict"] for r in g["derived"]]
+    assert rv.keep.astype(bool).tolist() == [r["keep_visualise"] for r in g["derived"]]
+    assert rs.class_id.tolist() == [r["class_id"] for r in g["derived"]]
+
+
+def test_transform_predictions_and_corners_match_oracle():
+    rng = np.random.default_rng(9)
+    logits = (rng.normal(size=(64, 17, 6)) * 3).astype(np.float32)
+    logits[0, 0] = [np.nan, 0, 0, 0, 0, 0]
+    logits[0, 1] = [100, -100, 100, -100, 100, -100]
+    for size in ((608, 608), (1024, 1024), (480, 640)):
+        ref = oracle.decode(logits.astype(np.float64), image_size=size)
+        rec = vd.decode_predictions(logits, image_size=size)
+        dec = vd.transform_predictions(logits, image_size=size)
+        ok = ~np.isnan(ref["decoded"])
+        assert np.abs(rec.decoded[ok] - ref["decoded"][ok]).max() < max(size) * 2e-6
+        assert np.array_equal(dec, rec.decoded, equal_nan=True)
+        assert np.isnan(rec.decoded[0, 0, 0]) and not rec.keep[0, 0]
+        # corners / ids / keep computed by the oracle from the GPU's own float32 decode must agree exactly
+        cid, cc, keep = oracle.threshold(rec.decoded.astype(np.float32))
+        fin = ~np.isnan(rec.decoded[..., 0])
+        assert np.array_equal(rec.class_id[fin], cid[fin]) and np.array_equal(rec.keep.astype(bool)[fin], keep[fin])
+        assert np.array_equal(rec.corners[fin], oracle.corners(rec.decoded.astype(np.float32), size)[fin])
+    e = vd.decode_predictions(np.zeros((0, 17, 6), np.float32))
+    assert e.decoded.shape == (0, 17, 6) and e.keep.shape == (0, 17)

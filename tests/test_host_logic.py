@@ -1,0 +1,96 @@
+"""CPU tests of the host side: the Keras weight table, initialisers, the builder helpers, and that the
+C-ABI library loads and exports every symbol include/vitdet_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from _util import ROOT, oracle, tiny_config
+import vision_transformer_detector_b200 as vd
+from vision_transformer_detector_b200 import _capi, keras_init
+
+
+def test_weight_table_matches_oracle_restatement():
+    for cfg in (vd.DetectorConfig(), tiny_config(),
+                vd.DetectorConfig(input_shape=(640, 640, 3), patch_size=16, embedding_dim=768, encoder_num_heads=12,
+                                  encoder_key_dim=64, encoder_repeat_times=12, encoder_mlp_quantities=3),
+                tiny_config(mlp_head_dense_mish_block_repeats=2)):
+        assert vd.weight_specs(cfg) == oracle.weight_table(cfg)
+
+
+def test_default_model_size():
+    specs = vd.weight_specs(vd.DetectorConfig())
+    assert len(specs) == 245                                     # notebook cell 7 progress bar "…/245"
+    assert sum(int(np.prod(s)) for _, s in specs) == 131_476_891
+
+
+def test_keras_initialisers():
+    rng = np.random.default_rng(0)
+    assert keras_init.compute_fans((28, 8, 40)) == (224.0, 1120.0)       # limit sqrt(6/1344)
+    assert keras_init.compute_fans((8, 40, 28)) == (320.0, 224.0)        # limit sqrt(6/544)
+    k = keras_init.init_weight(rng, "multi_head_attention/query/kernel", (28, 8, 40))
+    assert k.dtype == np.float32 and np.abs(k).max() <= np.sqrt(6 / 1344) and np.abs(k).max() > 0.9 * np.sqrt(6 / 1344)
+    assert not keras_init.init_weight(rng, "dense/bias", (17,)).any()
+    assert (keras_init.init_weight(rng, "layer_normalization/gamma", (28,)) == 1).all()
+    e = keras_init.init_weight(rng, "position_encoding/position_embedding/embeddings", (1296, 1))
+    assert np.abs(e).max() <= 0.05
+
+
+def test_builder_helpers_mirror_the_reference_signatures():
+    x = vd.vision_transformer_detector.Input((608, 608, 3))
+    e = vd.transformer_preprocessor(x, patch_size=17, embedding_dim=28, max_weight=10, clip_weight=True)
+    assert e.shape == (None, 1296, 28)
+    enc = vd.transformer_encoder(e, use_mish=True, num_heads=8, key_dim=40, dropout=None, mlp_quantities=8,
+                                 repeat_times=8, max_weight=10, clip_weight=True)
+    assert enc.shape == (None, 1296, 28)
+    h = vd.mlp_head(enc, use_mish=True, mlp_head_last_units=136, dense_layers_quantity=7, dense_mish_block_repeats=1,
+                    dropout=None, max_weight=10, clip_weight=True)
+    assert h.shape == (None, 17, 6)
+    with pytest.raises(NotImplementedError):
+        vd.transformer_encoder(e, use_mish=True, num_heads=8, key_dim=40, dropout=0.1, mlp_quantities=8,
+                               repeat_times=8, max_weight=10, clip_weight=True)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vitdet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(vitdet_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_capi.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/vitdet_b200.h but not exported"
+    assert declared == set(_capi.SYMBOLS), "ctypes table and header disagree"
+    assert _capi.load().vitdet_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_capi.Config) == 15 * 4
+    assert ctypes.sizeof(_capi.DecodeParams) == 7 * 4
+    assert ctypes.sizeof(_capi.Detections) == 5 * ctypes.sizeof(ctypes.c_void_p)
+    c = _capi.default_config()
+    assert (c.image_h, c.image_w, c.patch_size, c.embedding_dim, c.num_heads, c.key_dim) == (608, 608, 17, 28, 8, 40)
+    assert (c.mlp_quantities, c.repeat_times, c.head_last_units, c.head_dense_layers, c.head_block_repeats) == (8, 8, 136, 7, 1)
+    assert (c.use_mish, c.num_slots, c.classes) == (1, 17, 80) and abs(c.ln_epsilon - 1e-3) < 1e-9
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.VitdetError) as ei:
+        vd.create_vision_transformer_detector()
+    assert ei.value.code == _capi.E_NO_DEVICE
+    with pytest.raises(_capi.VitdetError):
+        vd.transform_predictions(np.zeros((1, 17, 6), np.float32))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "vision_transformer_detector_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "vitdet_oracle" not in text and "import oracle" not in text, f"{f} references the oracle"

@@ -1,0 +1,126 @@
+"""CPU tests of the oracle itself: pinned against the reference's golden vectors, and checked for
+internal consistency (float64 vs float32 vs the torch restatement, structural properties)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from _util import oracle, rel_err, tiny_config
+from vision_transformer_detector_b200 import random_weights
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "threshold_vectors.json")
+
+
+def test_threshold_rule_matches_reference_golden_vectors():
+    g = json.load(open(GOLDEN))
+    slots = np.array([r["slot"] for r in g["reference"]], np.float32)
+    cid, cc, keep = oracle.threshold(slots, strict=True)
+    assert keep.tolist() == [r["keep_strict"] for r in g["reference"]]
+    assert cid.tolist() == [r["class_id"] for r in g["reference"]]
+    # the confidences the reference's test docstrings quote: 79.255 -> 0.49, 79.3 -> 0.4
+    assert abs(cc[4] - 0.49) < 1e-4 and abs(cc[7] - 0.4) < 1e-4
+
+
+def test_threshold_rule_boundaries():
+    g = json.load(open(GOLDEN))
+    slots = np.array([r["slot"] for r in g["derived"]], np.float32)
+    cid, _, keep_s = oracle.threshold(slots, strict=True)
+    _, _, keep_v = oracle.threshold(slots, strict=False)
+    assert keep_s.tolist() == [r["keep_strict"] for r in g["derived"]]
+    assert keep_v.tolist() == [r["keep_visualise"] for r in g["derived"]]
+    assert cid.tolist() == [r["class_id"] for r in g["derived"]]
+
+
+def test_shape_facts_of_the_default_model():
+    """Facts pinned by the reference's notebook artefacts: 1296 tokens of 867,
+    245 weight tensors."""
+    cfg = oracle.default_config()
+    table = oracle.weight_table(cfg)
+    assert len(table) == 245
+    d = dict(table)
+    assert d["linear_projection/kernel"] == (867, 28)
+    assert d["position_encoding/position_embedding/embeddings"] == (1296, 1)
+    assert d["MLP_1_1/kernel"] == (28, 3584) and d["MLP_1_2/kernel"] == (3584, 1792) and d["MLP_8_8/kernel"] == (56, 28)
+    assert d["dense/kernel"] == (28, 17) and d["dense_1/kernel"] == (1296, 8704) and d["dense_7/kernel"] == (272, 136)
+    assert d["MLP_Head_no_Sigmoid/kernel"] == (136, 6)
+    assert d["multi_head_attention_7/query/kernel"] == (28, 8, 40) and d["multi_head_attention/attention_output/kernel"] == (8, 40, 28)
+    assert "layer_normalization_15/gamma" in d and "layer_normalization_16/gamma" not in d
+
+
+def test_extract_patches_same_padding():
+    """608 = 36*17 - 4: two zero rows/cols on every side; depth order (row, col, channel)."""
+    rng = np.random.default_rng(0)
+    img = rng.uniform(-1, 1, (1, 608, 608, 3))
+    p = oracle.extract_patches(img, 17)
+    assert p.shape == (1, 1296, 867)
+    first = p[0, 0].reshape(17, 17, 3)
+    assert np.all(first[:2] == 0) and np.all(first[:, :2] == 0)
+    assert np.array_equal(first[2:, 2:], img[0, :15, :15])
+    last = p[0, -1].reshape(17, 17, 3)
+    assert np.all(last[-2:] == 0) and np.all(last[:, -2:] == 0)
+    assert np.array_equal(last[:15, :15], img[0, -15:, -15:])
+    # token (1, 2) of the grid, element (r=3, c=5, ch=1)
+    tok = p[0, 1 * 36 + 2].reshape(17, 17, 3)
+    assert tok[3, 5, 1] == img[0, 17 * 1 + 3 - 2, 17 * 2 + 5 - 2, 1]
+    # no padding when the size divides
+    q = oracle.extract_patches(rng.uniform(-1, 1, (2, 32, 48, 3)), 16)
+    assert q.shape == (2, 6, 768)
+
+
+def test_head_reshape_is_a_flat_reinterpretation():
+    """det.py:461: Reshape((17, -1)) of the (T, 17) Dense output — slot i reads flat [i*T, (i+1)*T)."""
+    T = 12
+    y = np.arange(T * 17, dtype=np.float64).reshape(1, T, 17)
+    z = y.reshape(1, 17, -1)
+    # slot 0 is made of tokens 0.. interleaved with the 17 outputs, not of column 0
+    assert z[0, 1, 0] == T and z[0, 0, 1] == y[0, 0, 1] and z[0, 0, 11] == y[0, 0, 11] and z[0, 2, 0] == y[0, 1, 7]
+
+
+def test_activations_and_layernorm():
+    x = np.linspace(-20, 20, 101)
+    assert np.allclose(oracle.mish(x), x * np.tanh(np.log1p(np.exp(x))), atol=1e-12)
+    assert abs(oracle.gelu_tanh(np.array([1.0]))[0] - 0.841192) < 1e-5
+    r = np.random.default_rng(1).normal(size=(5, 28))
+    y = oracle.layer_norm(r, np.ones(28), np.zeros(28))
+    assert np.allclose(y.mean(-1), 0, atol=1e-12)
+    assert np.allclose(y.var(-1), r.var(-1) / (r.var(-1) + 1e-3), atol=1e-12)   # epsilon 1e-3, biased variance
+
+
+def test_transform_predictions():
+    l = np.array([[[0.0, 0.0, 0.0, 0.0, 0.0, 0.0], [50.0, -50.0, 2.0, -2.0, 1.0, -1.0]]])
+    d = oracle.transform_predictions(l)
+    assert np.allclose(d[0, 0], [0.5, 39.5, 304, 304, 304, 304])
+    s = 1 / (1 + np.exp(-np.array([2.0, -2.0, 1.0, -1.0])))
+    assert np.allclose(d[0, 1, 2:], s * 608) and d[0, 1, 0] > 0.999999 and d[0, 1, 1] < 1e-15
+    d2 = oracle.transform_predictions(l, image_size=(100, 200))
+    assert np.allclose(d2[0, 0, 2:], [100, 50, 50, 100])          # x,w scale by width; y,h by height
+
+
+@pytest.mark.parametrize("use_mish", [True, False])
+def test_f64_f32_torch_agree_on_a_tiny_model(use_mish):
+    cfg = tiny_config(use_mish=use_mish)
+    w = random_weights(cfg, seed=3, spread=True)
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-1, 1, (3, *cfg.input_shape)).astype(np.float32)
+    l64 = oracle.forward(w, cfg, img, np.float64)
+    l32 = oracle.forward(w, cfg, img, np.float32)
+    lt = oracle.forward_torch_f32(w, cfg, img)
+    assert l64.shape == (3, 17, 6)
+    assert rel_err(l32, l64) < 1e-4
+    assert rel_err(lt, l64) < 1e-4
+
+
+def test_attention_core_equals_mha_without_projections():
+    rng = np.random.default_rng(2)
+    B, T, H, d, D = 2, 9, 3, 8, 12
+    x = rng.normal(size=(B, T, D))
+    wq, wk, wv = (rng.normal(size=(D, H, d)) for _ in range(3))
+    bq, bk, bv = (rng.normal(size=(H, d)) for _ in range(3))
+    wo, bo = rng.normal(size=(H, d, D)), rng.normal(size=(D,))
+    full = oracle.multi_head_attention(x, wq, bq, wk, bk, wv, bv, wo, bo)
+    q = np.einsum("abc,cde->abde", x, wq) + bq
+    k = np.einsum("abc,cde->abde", x, wk) + bk
+    v = np.einsum("abc,cde->abde", x, wv) + bv
+    o = oracle.attention_core(q, k, v)
+    assert np.allclose(np.einsum("abcd,cde->abe", o, wo) + bo, full, atol=1e-12)

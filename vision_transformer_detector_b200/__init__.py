@@ -1,0 +1,23 @@
+"""vision_transformer_detector_b200 — B200-native (sm_100a) forward pass + anchor-free head decode of
+the ViT detector of westlake-moonlight/vision_transformer_detector, behind the reference's own Python
+entry points.  See DESIGN.md / INTEGRATION.md at the repository root."""
+from .vision_transformer_detector import (  # noqa: F401
+    Constants,
+    DetectionRecords,
+    DetectorConfig,
+    VisionTransformerDetector,
+    create_vision_transformer_detector,
+    decode_predictions,
+    mlp_head,
+    random_weights,
+    transform_predictions,
+    transformer_encoder,
+    transformer_preprocessor,
+    weight_specs,
+)
+
+__all__ = [
+    "Constants", "DetectionRecords", "DetectorConfig", "VisionTransformerDetector",
+    "create_vision_transformer_detector", "decode_predictions", "mlp_head", "random_weights",
+    "transform_predictions", "transformer_encoder", "transformer_preprocessor", "weight_specs",
+]

@@ -1,0 +1,246 @@
+// Shared device helpers for the sm_100a kernels of the ViT-detector hot path.
+//
+// Everything here is a thin wrapper around one PTX instruction (mbarrier, TMA bulk-tensor copy,
+// tcgen05 MMA / TMEM load / TMEM allocation) or a piece of activation arithmetic that several
+// kernels share.  No CUTLASS/CuTe types: the kernels in this directory are written against the
+// PTX ISA directly.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vitdet {
+
+// ---------------------------------------------------------------------------------------------
+// Activation ids shared by host and device (mirrors `use_mish` of the reference,
+// vision_transformer_detector.py:396-402 and :478-483).
+// ---------------------------------------------------------------------------------------------
+enum Act : int { ACT_NONE = 0, ACT_MISH = 1, ACT_GELU = 2 };
+
+// Mish(x) = x * tanh(softplus(x))  (tfa.activations.mish, reference det.py:129).
+// With n = e^x:  tanh(log(1+n)) = ((1+n)^2 - 1) / ((1+n)^2 + 1) = (n^2 + 2n) / (n^2 + 2n + 2),
+// which needs one ex2 and one rcp on the SFU instead of ex2 + lg2 + tanh.
+template <bool PRECISE>
+__device__ __forceinline__ float mish(float x) {
+    if (PRECISE) {
+        float n = expf(fminf(x, 30.f));
+        float a = n * (n + 2.f);
+        return x * (a / (a + 2.f));
+    } else {
+        float n = __expf(fminf(x, 20.f));
+        float a = n * (n + 2.f);
+        return x * __fdividef(a, a + 2.f);
+    }
+}
+
+// tfa.layers.GELU() default approximate=True (reference det.py:402):
+// 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) )).
+template <bool PRECISE>
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    float u = k0 * (x + k1 * x * x * x);
+    float t;
+    if (PRECISE) {
+        t = tanhf(u);
+    } else {
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    }
+    return 0.5f * x * (1.f + t);
+}
+
+template <int ACT, bool PRECISE>
+__device__ __forceinline__ float apply_act(float x) {
+    if (ACT == ACT_MISH) return mish<PRECISE>(x);
+    if (ACT == ACT_GELU) return gelu_tanh<PRECISE>(x);
+    return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory addresses, mbarriers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+// Makes mbarrier.init visible to the async proxy (TMA / tcgen05.commit arrive on these barriers).
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Generic-proxy writes to shared memory -> visible to async-proxy readers (TMA store, UMMA).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure reported
+// through the C ABI), never as a hung GPU.  try_wait suspends the thread in hardware for a
+// time slice, so the poll count is small on the normal path; the clock is only read after many
+// failed polls.  ~4 s at 2 GHz is far beyond any legitimate wait in these kernels.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 0x3fffu) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) — tiled 2-D loads into 128B-swizzled shared memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// L2 eviction-priority policies for TMA loads (createpolicy encodings used as immediates).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const CUtensorMap* map,
+                                                 uint32_t bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA issue, commit, TMEM -> register loads
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_result_addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, f32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// All previously issued tcgen05.mma of this thread arrive (once) on `bar` when they complete.
+// Implies tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i),
+// columns [col, col+32).  A warp may only touch the TMEM lane quadrant 32*(warp_id % 4).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle (what a TMA box of 64 bf16 x R rows
+// with CU_TENSOR_MAP_SWIZZLE_128B produces): rows are 128 B, 8 rows form a 1024 B swizzle atom.
+//   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (unused: 1)
+//   bits [32,46) stride byte offset >> 4 (1024 B between 8-row groups)
+//   bits [46,48) descriptor version = 1 (sm_100)     bits [61,64) layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16 with bf16 A/B (K-major both), f32 accumulator, M x N tile:
+//   [4,6) c_format = 1 (f32)   [7,10) a_format = 1 (bf16)   [10,13) b_format = 1 (bf16)
+//   bit 15 / 16 a_major / b_major = 0 (K-major)   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+}  // namespace vitdet

@@ -1,0 +1,1140 @@
+// Engine behind the C ABI (include/vitdet_b200.h): owns the packed weights and the workspace of one
+// detector instance and strings the kernels of this directory into the forward pass that
+// create_vision_transformer_detector builds as a Keras graph (reference det.py:498-583):
+//   transformer_preprocessor det.py:239-309 -> transformer_encoder det.py:312-414 -> mlp_head
+//   det.py:417-495 -> transform_predictions det.py:586-647 + thresholds det.py:2257-2283/1359-1384.
+//
+// Data layout in HBM (bf16 mode; the fp32 mode uses the same shapes with f32 elements):
+//   x     f32  [B*T, D4]        residual stream, kept in f32 for the whole batch (145 KB / image)
+//   per encoder chunk of Bc images (Mc = Bc*T rows), reused by every chunk:
+//   patch bf16 [Mc, P8]         extract_patches output, (row, col, channel) order
+//   y     bf16 [Mc, D8]         LayerNorm output (A operand of the QKV GEMM / first MLP GEMM)
+//   qkv   bf16 [Mc, 3*H*64]     q | k | v, one 64-wide (128-byte) slot per head, pads are zero
+//   ctx   bf16 [Mc, H*64]       attention output, same head pitch
+//   u0,u1 bf16 [Mc, w1],[Mc,w2] ping-pong activations of the MLP pyramid
+//   head (whole batch, R = B*S rows): s [B, T*S] == [R, T] (Reshape is a view), h0/h1 [R, u1],[R,u2]
+// Weights: every Dense kernel is stored transposed, W[N, K] with K contiguous (both tcgen05 operands
+// are K-major), once in bf16 and once in f32; biases in f32.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vitdet_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vitdet {
+
+// ------------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                               \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(VITDET_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define RC_TRY(expr)                   \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+constexpr int kHeadPitch = 64;   // elements per head slot in qkv / ctx (one 128-byte swizzle row of bf16)
+
+// ------------------------------------------------------------------------------------------------
+// weight packing kernels (run once per set_weight)
+// ------------------------------------------------------------------------------------------------
+// src: Keras Dense kernel viewed as row-major [K, N].  Element (k, n) goes to row rmap(n), column
+// cmap(k) of the transposed, padded destination, where
+//   rmap(n) = row_off + (n / gn) * pn + n % gn      cmap(k) = (k / gk) * pk + k % gk
+// (identity for plain Dense; gn = key_dim, pn = 64 scatters the heads of a q/k/v kernel to their
+// 64-wide slots; gk = key_dim, pk = 64 does the same for the K axis of attention_output).
+__global__ void pack_dense_kernel(const float* __restrict__ src, int K, int N, int gn, int pn, int row_off, int gk,
+                                  int pk, __nv_bfloat16* __restrict__ w16, int ld16, float* __restrict__ w32,
+                                  int ld32) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(K) * N) return;
+    const int k = static_cast<int>(idx / N), n = static_cast<int>(idx - static_cast<long long>(k) * N);
+    const int r = row_off + (n / gn) * pn + n % gn;
+    const int c = (k / gk) * pk + k % gk;
+    const float v = src[idx];
+    if (w16) w16[static_cast<size_t>(r) * ld16 + c] = __float2bfloat16_rn(v);
+    if (w32) w32[static_cast<size_t>(r) * ld32 + c] = v;
+}
+
+__global__ void pack_vec_kernel(const float* __restrict__ src, int N, int gn, int pn, int off, float* __restrict__ dst) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    dst[off + (n / gn) * pn + n % gn] = src[n];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds,
+                                   __nv_bfloat16* __restrict__ dst, int ldd) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(rows) * ldd) return;
+    const int r = static_cast<int>(idx / ldd), c = static_cast<int>(idx - static_cast<long long>(r) * ldd);
+    dst[idx] = __float2bfloat16_rn(c < cols ? src[static_cast<size_t>(r) * lds + c] : 0.f);
+}
+
+__global__ void pad_rows_f32_kernel(const float* __restrict__ src, int rows, int cols, int lds, float* __restrict__ dst,
+                                    int ldd) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(rows) * ldd) return;
+    const int r = static_cast<int>(idx / ldd), c = static_cast<int>(idx - static_cast<long long>(r) * ldd);
+    dst[idx] = c < cols ? src[static_cast<size_t>(r) * lds + c] : 0.f;
+}
+
+__global__ void unpad_rows_f32_kernel(const float* __restrict__ src, int rows, int cols, int lds, float* __restrict__ dst) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(rows) * cols) return;
+    const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx - static_cast<long long>(r) * cols);
+    dst[idx] = src[static_cast<size_t>(r) * lds + c];
+}
+
+// [B,T,H,d] f32 (q, k, v) -> fused [B*T, 3*H*hp] (bf16 or f32), pads zero.
+template <typename T>
+__global__ void pack_qkv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                long long rows, int H, int d, int hp, T* __restrict__ dst) {
+    const int ld = 3 * H * hp;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= rows * ld) return;
+    const long long r = idx / ld;
+    const int c = static_cast<int>(idx - r * ld);
+    const int sel = c / (H * hp), hh = (c / hp) % H, j = c % hp;
+    float val = 0.f;
+    if (j < d) {
+        const float* s = sel == 0 ? q : (sel == 1 ? k : v);
+        val = s[(r * H + hh) * d + j];
+    }
+    if (sizeof(T) == 2) reinterpret_cast<__nv_bfloat16*>(dst)[idx] = __float2bfloat16_rn(val);
+    else reinterpret_cast<float*>(dst)[idx] = val;
+}
+
+template <typename T>
+__global__ void unpack_ctx_kernel(const T* __restrict__ ctx, long long rows, int H, int d, int hp, float* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= rows * H * d) return;
+    const long long r = idx / (H * d);
+    const int c = static_cast<int>(idx - r * (H * d));
+    const int hh = c / d, j = c - hh * d;
+    const T* p = ctx + r * (H * hp) + hh * hp + j;
+    float val;
+    if (sizeof(T) == 2) val = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+    else val = *reinterpret_cast<const float*>(p);
+    out[idx] = val;
+}
+
+static inline int blocks_for(long long n, int bs = 256) { return static_cast<int>((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------------------------------------
+// device buffer helper
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            if (p) cudaFree(p);
+            p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0;
+        }
+        return *this;
+    }
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        need = (need + 255) / 256 * 256;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) return fail(VITDET_E_CUDA, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        bytes = need;
+        return 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+// One Dense layer in packed form.
+struct DenseW {
+    int N = 0, K = 0;          // packed GEMM shape (N includes head-slot pads for qkv, K for attention_output)
+    int ld16 = 0, ld32 = 0;
+    DevBuf w16, w32, bias;     // bias: f32 [round_up(N, 8)]
+    int alloc(int n, int k) {
+        N = n; K = k;
+        ld16 = round_up(k, 8);
+        ld32 = round_up(k, 4);
+        RC_TRY(w16.ensure(static_cast<size_t>(n) * ld16 * 2));
+        RC_TRY(w32.ensure(static_cast<size_t>(n) * ld32 * 4));
+        RC_TRY(bias.ensure(static_cast<size_t>(round_up(n, 8)) * 4));
+        CU_TRY(cudaMemset(w16.p, 0, w16.bytes));
+        CU_TRY(cudaMemset(w32.p, 0, w32.bytes));
+        CU_TRY(cudaMemset(bias.p, 0, bias.bytes));
+        return 0;
+    }
+};
+
+// How one Keras variable maps into the packed storage.
+struct WeightSlot {
+    std::string name;
+    int ndim = 0;
+    int64_t shape[4] = {0, 0, 0, 0};
+    int64_t count = 0;
+    enum Kind { DENSE_KERNEL, DENSE_BIAS, VEC } kind = VEC;
+    DenseW* dense = nullptr;   // DENSE_*
+    int K = 0, N = 0;          // source [K, N] view of a kernel / N of a bias
+    int gn = 1, pn = 1, row_off = 0, gk = 1, pk = 1;
+    float* vec_dst = nullptr;  // VEC: plain f32 copy target (LayerNorm gamma/beta, position embedding, f32-only kernels)
+    bool vec_transpose = false;   // VEC kernels kept in f32 as [N, K] (head slot projection, final Dense(6))
+    bool set = false;
+    std::vector<float> master;    // Keras-layout copy returned by get_weight
+};
+
+struct BlockW {
+    DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+    DenseW qkv, out;
+    std::vector<DenseW> mlp;
+};
+
+struct PlanSet;   // per (mode, rows) cached TMA descriptors
+
+}  // namespace vitdet
+
+using namespace vitdet;
+
+struct vitdet_handle {
+    vitdet_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    int gh = 0, gw = 0, T = 0, P = 0, D = 0, H = 0, d = 0, S = 0;
+    int act = ACT_MISH;
+    int chunk = 64;
+
+    // weights
+    DenseW proj;
+    DevBuf pos;                         // f32 [T]
+    std::vector<BlockW> blocks;
+    DevBuf head_slot_w, head_slot_b;    // f32 [S, D], [S]
+    std::vector<DenseW> head;
+    DevBuf tail_w, tail_b;              // f32 [6, U], [6]
+    int tail_U = 0;
+    std::vector<WeightSlot> slots;
+    std::map<std::string, int> slot_index;
+    DevBuf stage;                       // device staging for set_weight
+
+    // workspace (grow-only)
+    DevBuf x, patch, y, qkv, ctx, u0, u1, s, h0, h1;
+    // cached plans
+    struct EncPlans {
+        bool valid = false;
+        const void* base_sig[8] = {};
+        TcGemmPlan proj, head_dummy;
+        std::vector<TcGemmPlan> qkv, out;
+        std::vector<std::vector<TcGemmPlan>> mlp;
+        std::vector<AttnPlan> attn;
+    };
+    std::map<int, EncPlans> enc_plans;      // key: images in the chunk
+    struct HeadPlans {
+        bool valid = false;
+        const void* base_sig[4] = {};
+        std::vector<TcGemmPlan> dense;
+    };
+    std::map<int, HeadPlans> head_plans;    // key: batch
+
+    // profiling (off by default): CUDA events around the launches of the categories in prof_mask
+    uint32_t prof_mask = 0;
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[32] = {};
+    long long prof_n[32] = {};
+    long long launches = 0;             // kernels launched by forward_impl since the last reset
+
+    // pinned staging + device buffers for predict_host
+    void* pin_in = nullptr; size_t pin_in_bytes = 0;
+    void* pin_out = nullptr; size_t pin_out_bytes = 0;
+    DevBuf dev_in, dev_out;
+
+    ~vitdet_handle() {
+        for (auto& r : prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : prof_pool) cudaEventDestroy(e);
+        if (pin_in) cudaFreeHost(pin_in);
+        if (pin_out) cudaFreeHost(pin_out);
+    }
+};
+
+namespace vitdet {
+
+// ------------------------------------------------------------------------------------------------
+// configuration -> weight table (Keras `model.weights` order and names)
+// ------------------------------------------------------------------------------------------------
+static std::string keras_name(const char* base, int index) {
+    // keras.backend.clear_session() (det.py:548) resets the auto-name counters, so the first
+    // instance of a layer class is un-suffixed and instance i >= 1 is "<base>_<i>".
+    if (index == 0) return base;
+    return std::string(base) + "_" + std::to_string(index);
+}
+
+static void add_slot(vitdet_handle* h, WeightSlot&& s) {
+    s.count = 1;
+    for (int i = 0; i < s.ndim; ++i) s.count *= s.shape[i];
+    h->slot_index[s.name] = static_cast<int>(h->slots.size());
+    h->slots.push_back(std::move(s));
+}
+
+static void add_dense_slots(vitdet_handle* h, const std::string& layer, DenseW* w, int K, int N) {
+    WeightSlot k;
+    k.name = layer + "/kernel"; k.ndim = 2; k.shape[0] = K; k.shape[1] = N;
+    k.kind = WeightSlot::DENSE_KERNEL; k.dense = w; k.K = K; k.N = N;
+    k.gn = N; k.pn = N; k.gk = K; k.pk = K;
+    add_slot(h, std::move(k));
+    WeightSlot b;
+    b.name = layer + "/bias"; b.ndim = 1; b.shape[0] = N;
+    b.kind = WeightSlot::DENSE_BIAS; b.dense = w; b.N = N; b.gn = N; b.pn = N;
+    add_slot(h, std::move(b));
+}
+
+static int add_vec_slot(vitdet_handle* h, const std::string& name, DevBuf* buf, int ndim, const int64_t* shape,
+                        bool transpose = false) {
+    WeightSlot v;
+    v.name = name; v.ndim = ndim;
+    int64_t cnt = 1;
+    for (int i = 0; i < ndim; ++i) { v.shape[i] = shape[i]; cnt *= shape[i]; }
+    RC_TRY(buf->ensure(static_cast<size_t>(cnt) * 4));
+    CU_TRY(cudaMemset(buf->p, 0, buf->bytes));
+    v.kind = WeightSlot::VEC; v.vec_dst = buf->as<float>(); v.vec_transpose = transpose;
+    if (transpose) { v.K = static_cast<int>(shape[0]); v.N = static_cast<int>(shape[1]); }
+    add_slot(h, std::move(v));
+    return 0;
+}
+
+static int build_weight_table(vitdet_handle* h) {
+    const vitdet_config& c = h->cfg;
+    const int D = h->D, H = h->H, d = h->d, T = h->T, P = h->P, S = h->S, hp = kHeadPitch;
+
+    // transformer_preprocessor: Dense 'linear_projection' (det.py:297) then PositionEncoding's
+    // Embedding(T, 1) 'position_encoding/position_embedding' (det.py:148-151, 291-293).
+    RC_TRY(h->proj.alloc(D, P));
+    add_dense_slots(h, "linear_projection", &h->proj, P, D);
+    { const int64_t shp[2] = {T, 1}; RC_TRY(add_vec_slot(h, "position_encoding/position_embedding/embeddings", &h->pos, 2, shp)); }
+
+    h->blocks.resize(c.repeat_times);
+    for (int i = 0; i < c.repeat_times; ++i) {
+        BlockW& b = h->blocks[i];
+        const std::string ln1 = keras_name("layer_normalization", 2 * i);
+        const std::string ln2 = keras_name("layer_normalization", 2 * i + 1);
+        const std::string mha = keras_name("multi_head_attention", i);
+        const int64_t shpD[1] = {D};
+        RC_TRY(add_vec_slot(h, ln1 + "/gamma", &b.ln1_g, 1, shpD));
+        RC_TRY(add_vec_slot(h, ln1 + "/beta", &b.ln1_b, 1, shpD));
+        // MultiHeadAttention (det.py:364-369): q/k/v EinsumDense kernels (D, H, d) + bias (H, d),
+        // fused into one [3*H*64, D] GEMM weight; attention_output kernel (H, d, D) + bias (D).
+        RC_TRY(b.qkv.alloc(3 * H * hp, D));
+        const char* sel[3] = {"query", "key", "value"};
+        for (int s = 0; s < 3; ++s) {
+            WeightSlot k;
+            k.name = mha + "/" + sel[s] + "/kernel"; k.ndim = 3; k.shape[0] = D; k.shape[1] = H; k.shape[2] = d;
+            k.kind = WeightSlot::DENSE_KERNEL; k.dense = &b.qkv; k.K = D; k.N = H * d;
+            k.gn = d; k.pn = hp; k.row_off = s * H * hp; k.gk = D; k.pk = D;
+            add_slot(h, std::move(k));
+            WeightSlot bb;
+            bb.name = mha + "/" + sel[s] + "/bias"; bb.ndim = 2; bb.shape[0] = H; bb.shape[1] = d;
+            bb.kind = WeightSlot::DENSE_BIAS; bb.dense = &b.qkv; bb.N = H * d; bb.gn = d; bb.pn = hp; bb.row_off = s * H * hp;
+            add_slot(h, std::move(bb));
+        }
+        RC_TRY(b.out.alloc(D, H * hp));
+        {
+            WeightSlot k;
+            k.name = mha + "/attention_output/kernel"; k.ndim = 3; k.shape[0] = H; k.shape[1] = d; k.shape[2] = D;
+            k.kind = WeightSlot::DENSE_KERNEL; k.dense = &b.out; k.K = H * d; k.N = D;
+            k.gn = D; k.pn = D; k.gk = d; k.pk = hp;
+            add_slot(h, std::move(k));
+            WeightSlot bb;
+            bb.name = mha + "/attention_output/bias"; bb.ndim = 1; bb.shape[0] = D;
+            bb.kind = WeightSlot::DENSE_BIAS; bb.dense = &b.out; bb.N = D; bb.gn = D; bb.pn = D;
+            add_slot(h, std::move(bb));
+        }
+        RC_TRY(add_vec_slot(h, ln2 + "/gamma", &b.ln2_g, 1, shpD));
+        RC_TRY(add_vec_slot(h, ln2 + "/beta", &b.ln2_b, 1, shpD));
+        // MLP pyramid (det.py:385-394): widths D * 2^(q-1) ... D.
+        b.mlp.resize(c.mlp_quantities);
+        int in = D;
+        for (int j = 0; j < c.mlp_quantities; ++j) {
+            const int units = D << (c.mlp_quantities - 1 - j);
+            RC_TRY(b.mlp[j].alloc(units, in));
+            add_dense_slots(h, "MLP_" + std::to_string(i + 1) + "_" + std::to_string(j + 1), &b.mlp[j], in, units);
+            in = units;
+        }
+    }
+
+    // mlp_head (det.py:454-493): auto-named 'dense', 'dense_1', ... then 'MLP_Head_no_Sigmoid'.
+    int dense_idx = 0;
+    {
+        const std::string nm = keras_name("dense", dense_idx++);
+        const int64_t shpk[2] = {D, S}; const int64_t shpb[1] = {S};
+        RC_TRY(add_vec_slot(h, nm + "/kernel", &h->head_slot_w, 2, shpk, true));
+        RC_TRY(add_vec_slot(h, nm + "/bias", &h->head_slot_b, 1, shpb));
+    }
+    const int n_head = c.head_dense_layers * c.head_block_repeats;
+    h->head.resize(n_head);
+    int in = T, li = 0;
+    for (int k = c.head_dense_layers - 1; k >= 0; --k) {
+        const int units = c.head_last_units << k;
+        for (int r = 0; r < c.head_block_repeats; ++r, ++li) {
+            RC_TRY(h->head[li].alloc(units, in));
+            add_dense_slots(h, keras_name("dense", dense_idx++), &h->head[li], in, units);
+            in = units;
+        }
+    }
+    h->tail_U = in;
+    {
+        const int64_t shpk[2] = {in, 6}; const int64_t shpb[1] = {6};
+        RC_TRY(add_vec_slot(h, "MLP_Head_no_Sigmoid/kernel", &h->tail_w, 2, shpk, true));
+        RC_TRY(add_vec_slot(h, "MLP_Head_no_Sigmoid/bias", &h->tail_b, 1, shpb));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense dispatch
+// ------------------------------------------------------------------------------------------------
+struct DenseCall {
+    const void* A; int lda;
+    const DenseW* w;
+    const float* pos = nullptr; int pos_period = 1;
+    const float* resid = nullptr; int ldr = 0;
+    void* out; int ldc; int out_f32; int act;
+    int M;
+};
+
+static GemmDesc make_desc(const DenseCall& c, int mode) {
+    GemmDesc g;
+    g.A = c.A; g.lda = c.lda;
+    g.W = mode == VITDET_MODE_BF16 ? c.w->w16.p : c.w->w32.p;
+    g.ldw = mode == VITDET_MODE_BF16 ? c.w->ld16 : c.w->ld32;
+    g.M = c.M; g.N = c.w->N; g.K = c.w->K;
+    g.bias = c.w->bias.as<float>();
+    g.pos = c.pos; g.pos_period = c.pos_period;
+    g.resid = c.resid; g.ldr = c.ldr;
+    g.out = c.out; g.ldc = c.ldc; g.out_f32 = c.out_f32; g.act = c.act;
+    return g;
+}
+
+static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
+    GemmDesc g = make_desc(c, VITDET_MODE_BF16);
+    int rc = tc_gemm_make_plan(plan, g, h->num_sms);
+    if (rc) return fail(VITDET_E_INVALID, "tc_gemm_make_plan(M=%d N=%d K=%d lda=%d ldc=%d) failed: %d", g.M, g.N, g.K, g.lda, g.ldc, rc);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct Dims {
+    int es;          // activation element size
+    int D4, D8, Pld, w_qkv, w_ctx, w_u0, w_u1, w_h0, w_h1;
+};
+
+static Dims dims_for(const vitdet_handle* h, int mode) {
+    Dims m;
+    const vitdet_config& c = h->cfg;
+    m.es = mode == VITDET_MODE_BF16 ? 2 : 4;
+    m.D4 = round_up(h->D, 4);
+    m.D8 = round_up(h->D, 8);
+    m.Pld = round_up(h->P, 8);
+    m.w_qkv = 3 * h->H * kHeadPitch;
+    m.w_ctx = h->H * kHeadPitch;
+    // MLP ping-pong: layer j writes buffer j & 1; widest even / odd layer outputs.
+    m.w_u0 = 8; m.w_u1 = 8;
+    for (int j = 0; j + 1 < c.mlp_quantities; ++j) {
+        const int units = round_up(h->D << (c.mlp_quantities - 1 - j), 8);
+        if (j & 1) m.w_u1 = units > m.w_u1 ? units : m.w_u1; else m.w_u0 = units > m.w_u0 ? units : m.w_u0;
+    }
+    m.w_h0 = 8; m.w_h1 = 8;
+    for (size_t i = 0; i < h->head.size(); ++i) {
+        const int units = round_up(h->head[i].N, 8);
+        if (i & 1) m.w_h1 = units > m.w_h1 ? units : m.w_h1; else m.w_h0 = units > m.w_h0 ? units : m.w_h0;
+    }
+    return m;
+}
+
+static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+
+static size_t workspace_bytes(const vitdet_handle* h, int B, int mode) {
+    const Dims m = dims_for(h, mode);
+    const size_t bc = static_cast<size_t>(B < h->chunk ? B : h->chunk);
+    const size_t Mc = bc * h->T, R = static_cast<size_t>(B) * h->S;
+    size_t tot = 0;
+    tot += a256(static_cast<size_t>(B) * h->T * m.D4 * 4);
+    tot += a256(Mc * m.Pld * m.es) + a256(Mc * m.D8 * m.es) + a256(Mc * m.w_qkv * m.es) + a256(Mc * m.w_ctx * m.es);
+    tot += a256(Mc * m.w_u0 * m.es) + a256(Mc * m.w_u1 * m.es);
+    tot += a256(R * h->T * m.es) + a256(R * m.w_h0 * m.es) + a256(R * m.w_h1 * m.es);
+    return tot;
+}
+
+static int ensure_workspace(vitdet_handle* h, int B, int mode) {
+    const Dims m = dims_for(h, mode);
+    const size_t bc = static_cast<size_t>(B < h->chunk ? B : h->chunk);
+    const size_t Mc = bc * h->T, R = static_cast<size_t>(B) * h->S;
+    const void* before[10] = {h->x.p, h->patch.p, h->y.p, h->qkv.p, h->ctx.p, h->u0.p, h->u1.p, h->s.p, h->h0.p, h->h1.p};
+    RC_TRY(h->x.ensure(static_cast<size_t>(B) * h->T * m.D4 * 4));
+    RC_TRY(h->patch.ensure(Mc * m.Pld * m.es));
+    RC_TRY(h->y.ensure(Mc * m.D8 * m.es));
+    RC_TRY(h->qkv.ensure(Mc * m.w_qkv * m.es));
+    RC_TRY(h->ctx.ensure(Mc * m.w_ctx * m.es));
+    RC_TRY(h->u0.ensure(Mc * m.w_u0 * m.es));
+    RC_TRY(h->u1.ensure(Mc * m.w_u1 * m.es));
+    RC_TRY(h->s.ensure(R * h->T * m.es));
+    RC_TRY(h->h0.ensure(R * m.w_h0 * m.es));
+    RC_TRY(h->h1.ensure(R * m.w_h1 * m.es));
+    const void* after[10] = {h->x.p, h->patch.p, h->y.p, h->qkv.p, h->ctx.p, h->u0.p, h->u1.p, h->s.p, h->h0.p, h->h1.p};
+    for (int i = 0; i < 10; ++i) {
+        if (before[i] != after[i]) {     // a buffer moved: every cached TMA descriptor is stale
+            h->enc_plans.clear();
+            h->head_plans.clear();
+            break;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans (bf16 mode): TMA descriptors for every GEMM / attention launch of one encoder chunk
+// ------------------------------------------------------------------------------------------------
+static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep) {
+    const Dims m = dims_for(h, VITDET_MODE_BF16);
+    const vitdet_config& c = h->cfg;
+    const int Mc = bc * h->T;
+    const int L = c.repeat_times, q = c.mlp_quantities;
+    float* xdummy = h->x.as<float>();
+
+    DenseCall pc{h->patch.p, m.Pld, &h->proj, h->pos.as<float>(), h->T, nullptr, 0, xdummy, m.D4, 1, ACT_NONE, Mc};
+    RC_TRY(plan_dense(h, pc, &ep->proj));
+
+    ep->qkv.resize(L); ep->out.resize(L); ep->attn.resize(L); ep->mlp.assign(L, std::vector<TcGemmPlan>(q));
+    for (int i = 0; i < L; ++i) {
+        BlockW& b = h->blocks[i];
+        DenseCall qc{h->y.p, m.D8, &b.qkv, nullptr, 1, nullptr, 0, h->qkv.p, m.w_qkv, 0, ACT_NONE, Mc};
+        RC_TRY(plan_dense(h, qc, &ep->qkv[i]));
+        AttnDesc ad;
+        ad.qkv = h->qkv.p; ad.ldq = m.w_qkv; ad.ctx = h->ctx.p; ad.ldo = m.w_ctx;
+        ad.B = bc; ad.T = h->T; ad.H = h->H; ad.d = h->d; ad.hp = kHeadPitch;
+        ad.scale = 1.f / sqrtf(static_cast<float>(h->d));
+        int rc = attn_bf16_make_plan(&ep->attn[i], ad);
+        if (rc) return fail(VITDET_E_INVALID, "attn_bf16_make_plan failed: %d", rc);
+        DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, xdummy, m.D4, xdummy, m.D4, 1, ACT_NONE, Mc};
+        RC_TRY(plan_dense(h, oc, &ep->out[i]));
+        const void* a = h->y.p; int lda = m.D8;
+        for (int j = 0; j < q; ++j) {
+            const bool last = j == q - 1;
+            void* o = last ? static_cast<void*>(xdummy) : ((j & 1) ? h->u1.p : h->u0.p);
+            const int ldo = last ? m.D4 : round_up(b.mlp[j].N, 8);
+            DenseCall mc{a, lda, &b.mlp[j], nullptr, 1, last ? xdummy : nullptr, last ? m.D4 : 0, o, ldo, last ? 1 : 0, h->act, Mc};
+            RC_TRY(plan_dense(h, mc, &ep->mlp[i][j]));
+            a = o; lda = ldo;
+        }
+    }
+    ep->valid = true;
+    return 0;
+}
+
+static int build_head_plans(vitdet_handle* h, int B, vitdet_handle::HeadPlans* hp) {
+    const int R = B * h->S;
+    hp->dense.resize(h->head.size());
+    const void* a = h->s.p; int lda = h->T;
+    for (size_t i = 0; i < h->head.size(); ++i) {
+        void* o = (i & 1) ? h->h1.p : h->h0.p;
+        const int ldo = round_up(h->head[i].N, 8);
+        DenseCall hc{a, lda, &h->head[i], nullptr, 1, nullptr, 0, o, ldo, 0, h->act, R};
+        RC_TRY(plan_dense(h, hc, &hp->dense[i]));
+        a = o; lda = ldo;
+    }
+    hp->valid = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling scopes
+// ------------------------------------------------------------------------------------------------
+enum ProfCat { PC_PATCHIFY = 0, PC_PROJ, PC_LN, PC_QKV, PC_ATTN, PC_OUT, PC_HEAD_SLOTS, PC_HEAD_GEMM, PC_HEAD_TAIL, PC_MLP0 = 9 };
+
+static const char* prof_cat_name(int c) {
+    static const char* base[] = {"patchify", "gemm_linear_projection", "layernorm", "gemm_qkv", "attention",
+                                 "gemm_attention_output", "head_slots", "gemm_head", "head_tail_decode"};
+    static char buf[32][24];
+    if (c < 0 || c >= 32) return "";
+    if (c < PC_MLP0) return base[c];
+    snprintf(buf[c], sizeof(buf[c]), "gemm_mlp_%d", c - PC_MLP0 + 1);
+    return buf[c];
+}
+
+static cudaEvent_t prof_event(vitdet_handle* h) {
+    if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    vitdet_handle* h; int cat; cudaStream_t st; cudaEvent_t a = nullptr; bool on;
+    ProfScope(vitdet_handle* h_, int cat_, cudaStream_t st_) : h(h_), cat(cat_ < 32 ? cat_ : 31), st(st_) {
+        ++h->launches;
+        on = (h->prof_mask >> cat) & 1u;
+        if (on) { a = prof_event(h); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEvent_t b = prof_event(h); cudaEventRecord(b, st); h->prof_pending.push_back({cat, a, b}); }
+    }
+};
+
+static int prof_collect(vitdet_handle* h) {
+    for (auto& r : h->prof_pending) {
+        CU_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        h->prof_ms[r.cat] += ms; h->prof_n[r.cat] += 1;
+        h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
+    }
+    h->prof_pending.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int launch_tc(TcGemmPlan plan /*by value: out / resid are patched per launch*/, void* out, const float* resid,
+                     cudaStream_t st) {
+    plan.desc.out = out;
+    plan.desc.resid = resid;
+    cudaError_t e = tc_gemm_launch(plan, st);
+    if (e != cudaSuccess) return fail(VITDET_E_CUDA, "tc_gemm_launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int launch_simt(const DenseCall& c, cudaStream_t st) {
+    GemmDesc g = make_desc(c, VITDET_MODE_FP32);
+    cudaError_t e = simt_gemm_launch(g, st);
+    if (e != cudaSuccess) return fail(VITDET_E_CUDA, "simt_gemm_launch(M=%d N=%d K=%d) failed: %s", g.M, g.N, g.K, cudaGetErrorString(e));
+    return 0;
+}
+
+static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, float* logits,
+                        const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st) {
+    if (!h || !images || B <= 0) return fail(VITDET_E_INVALID, "forward: bad arguments");
+    if (mode != VITDET_MODE_BF16 && mode != VITDET_MODE_FP32) return fail(VITDET_E_INVALID, "forward: unknown mode %d", mode);
+    for (const WeightSlot& s : h->slots)
+        if (!s.set) return fail(VITDET_E_UNSET, "forward: weight '%s' has not been set", s.name.c_str());
+    const vitdet_config& c = h->cfg;
+    const bool bf = mode == VITDET_MODE_BF16;
+    if (bf && (h->T % 8)) return fail(VITDET_E_INVALID, "bf16 mode needs tokens %% 8 == 0 (tokens = %d)", h->T);
+    if (!bf && (h->T % 4)) return fail(VITDET_E_INVALID, "fp32 mode needs tokens %% 4 == 0 (tokens = %d)", h->T);
+    RC_TRY(ensure_workspace(h, B, mode));
+    const Dims m = dims_for(h, mode);
+    const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
+    const int out_f32_act = bf ? 0 : 1;
+
+    for (int c0 = 0; c0 < B; c0 += h->chunk) {
+        const int bc = (B - c0) < h->chunk ? (B - c0) : h->chunk;
+        const int Mc = bc * T;
+        float* x = h->x.as<float>() + static_cast<size_t>(c0) * T * m.D4;
+        vitdet_handle::EncPlans* ep = nullptr;
+        if (bf) {
+            ep = &h->enc_plans[bc];
+            if (!ep->valid) RC_TRY(build_enc_plans(h, bc, ep));
+        }
+        const float* img = images + static_cast<size_t>(c0) * c.image_h * c.image_w * 3;
+        { ProfScope ps(h, PC_PATCHIFY, st);
+        CU_TRY(patchify_launch(img, bc, c.image_h, c.image_w, c.patch_size, h->patch.p, bf ? m.Pld : round_up(h->P, 4), out_f32_act, st)); }
+        if (bf) {
+            ProfScope ps(h, PC_PROJ, st);
+            RC_TRY(launch_tc(ep->proj, x, nullptr, st));
+        } else {
+            ProfScope ps(h, PC_PROJ, st);
+            DenseCall pc{h->patch.p, round_up(h->P, 4), &h->proj, h->pos.as<float>(), T, nullptr, 0, x, m.D4, 1, ACT_NONE, Mc};
+            RC_TRY(launch_simt(pc, st));
+        }
+        for (int i = 0; i < L; ++i) {
+            BlockW& b = h->blocks[i];
+            const int ldy = bf ? m.D8 : m.D4;
+            { ProfScope ps(h, PC_LN, st);
+            CU_TRY(layernorm_launch(x, m.D4, b.ln1_g.as<float>(), b.ln1_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
+            if (bf) {
+                { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_tc(ep->qkv[i], h->qkv.p, nullptr, st)); }
+                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_bf16_launch(ep->attn[i], st)); }
+                { ProfScope ps(h, PC_OUT, st); RC_TRY(launch_tc(ep->out[i], x, x, st)); }
+            } else {
+                DenseCall qc{h->y.p, ldy, &b.qkv, nullptr, 1, nullptr, 0, h->qkv.p, m.w_qkv, 1, ACT_NONE, Mc};
+                { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_simt(qc, st)); }
+                AttnDesc ad;
+                ad.qkv = h->qkv.p; ad.ldq = m.w_qkv; ad.ctx = h->ctx.p; ad.ldo = m.w_ctx;
+                ad.B = bc; ad.T = T; ad.H = h->H; ad.d = h->d; ad.hp = kHeadPitch;
+                ad.scale = 1.f / sqrtf(static_cast<float>(h->d));
+                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_f32_launch(ad, st)); }
+                DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, x, m.D4, x, m.D4, 1, ACT_NONE, Mc};
+                { ProfScope ps(h, PC_OUT, st); RC_TRY(launch_simt(oc, st)); }
+            }
+            { ProfScope ps(h, PC_LN, st);
+            CU_TRY(layernorm_launch(x, m.D4, b.ln2_g.as<float>(), b.ln2_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
+            const void* a = h->y.p; int lda = ldy;
+            for (int j = 0; j < q; ++j) {
+                const bool last = j == q - 1;
+                void* o = last ? static_cast<void*>(x) : ((j & 1) ? h->u1.p : h->u0.p);
+                ProfScope ps(h, PC_MLP0 + j, st);
+                if (bf) {
+                    RC_TRY(launch_tc(ep->mlp[i][j], o, last ? x : nullptr, st));
+                } else {
+                    const int ldo = last ? m.D4 : round_up(b.mlp[j].N, 4);
+                    DenseCall mc{a, lda, &b.mlp[j], nullptr, 1, last ? x : nullptr, last ? m.D4 : 0, o, ldo, 1, h->act, Mc};
+                    RC_TRY(launch_simt(mc, st));
+                    a = o; lda = ldo;
+                }
+            }
+        }
+    }
+
+    // mlp_head over the whole batch (det.py:454-493).
+    const int R = B * h->S;
+    { ProfScope ps(h, PC_HEAD_SLOTS, st);
+    CU_TRY(head_slots_launch(h->x.as<float>(), m.D4, h->head_slot_w.as<float>(), h->head_slot_b.as<float>(), B * T, h->D, h->S,
+                             h->s.p, out_f32_act, st)); }
+    const void* a = h->s.p; int lda = T;
+    if (bf) {
+        vitdet_handle::HeadPlans* hp = &h->head_plans[B];
+        if (!hp->valid) RC_TRY(build_head_plans(h, B, hp));
+        for (size_t i = 0; i < h->head.size(); ++i) {
+            void* o = (i & 1) ? h->h1.p : h->h0.p;
+            ProfScope ps(h, PC_HEAD_GEMM, st);
+            RC_TRY(launch_tc(hp->dense[i], o, nullptr, st));
+            a = o; lda = round_up(h->head[i].N, 8);
+        }
+    } else {
+        for (size_t i = 0; i < h->head.size(); ++i) {
+            void* o = (i & 1) ? h->h1.p : h->h0.p;
+            const int ldo = round_up(h->head[i].N, 4);
+            DenseCall hc{a, lda, &h->head[i], nullptr, 1, nullptr, 0, o, ldo, 1, h->act, R};
+            ProfScope ps(h, PC_HEAD_GEMM, st);
+            RC_TRY(launch_simt(hc, st));
+            a = o; lda = ldo;
+        }
+    }
+    DecodeParams dp;
+    DecodeOut dout;
+    dout.logits = logits;
+    if (dpar) {
+        dp.obj_thr = dpar->objectness_threshold; dp.cls_thr = dpar->classification_threshold;
+        dp.strict = dpar->strict; dp.img_h = dpar->image_h; dp.img_w = dpar->image_w; dp.classes = dpar->classes;
+        dp.apply_transform = 1;   // the head emits raw logits
+    }
+    if (det) {
+        dout.decoded = det->decoded; dout.class_id = det->class_id; dout.class_conf = det->class_conf;
+        dout.keep = det->keep; dout.corners = det->corners;
+    }
+    ProfScope ps(h, PC_HEAD_TAIL, st);
+    CU_TRY(head_tail_launch(a, lda, out_f32_act, h->tail_w.as<float>(), h->tail_b.as<float>(), R, h->tail_U, dp, dout, st));
+    return 0;
+}
+
+}  // namespace vitdet
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int vitdet_abi_version(void) { return VITDET_ABI_VERSION; }
+const char* vitdet_last_error(void) { return g_err; }
+
+void vitdet_default_config(vitdet_config* c) {
+    if (!c) return;
+    c->image_h = 608; c->image_w = 608;       // Constants.MODEL_IMAGE_SIZE det.py:22
+    c->patch_size = 17; c->embedding_dim = 28; c->num_heads = 8; c->key_dim = 40;     // det.py:499-500
+    c->mlp_quantities = 8; c->repeat_times = 8;                                        // det.py:501-502
+    c->head_last_units = 136; c->head_dense_layers = 7; c->head_block_repeats = 1;     // det.py:503-504
+    c->use_mish = 1;                                                                   // det.py:505
+    c->num_slots = 17; c->classes = 80;                                                // det.py:28, :20
+    c->ln_epsilon = 1e-3f;                                                             // keras default
+}
+
+int vitdet_create(const vitdet_config* cfg, vitdet_handle** out) {
+    if (!cfg || !out) return fail(VITDET_E_INVALID, "vitdet_create: null argument");
+    *out = nullptr;
+    const vitdet_config& c = *cfg;
+    if (c.image_h <= 0 || c.image_w <= 0 || c.patch_size <= 0 || c.embedding_dim <= 0 || c.num_heads <= 0 ||
+        c.key_dim <= 0 || c.mlp_quantities <= 0 || c.repeat_times <= 0 || c.head_last_units <= 0 ||
+        c.head_dense_layers <= 0 || c.head_block_repeats <= 0 || c.num_slots <= 0 || c.classes <= 1)
+        return fail(VITDET_E_INVALID, "vitdet_create: every size in the configuration must be positive");
+    if (c.key_dim > kHeadPitch) return fail(VITDET_E_INVALID, "encoder_key_dim %d > %d is not supported by this build", c.key_dim, kHeadPitch);
+    if (c.embedding_dim > 2048) return fail(VITDET_E_INVALID, "embedding_dim %d > 2048 is not supported by this build", c.embedding_dim);
+    if (c.mlp_quantities > 20 || c.head_dense_layers > 20) return fail(VITDET_E_INVALID, "pyramid depth out of range");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VITDET_E_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    }
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(VITDET_E_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, prop.major, prop.minor);
+
+    vitdet_handle* h = new vitdet_handle();
+    h->cfg = c;
+    h->device = dev;
+    h->num_sms = prop.multiProcessorCount;
+    h->gh = (c.image_h + c.patch_size - 1) / c.patch_size;
+    h->gw = (c.image_w + c.patch_size - 1) / c.patch_size;
+    h->T = h->gh * h->gw;
+    h->P = 3 * c.patch_size * c.patch_size;
+    h->D = c.embedding_dim; h->H = c.num_heads; h->d = c.key_dim; h->S = c.num_slots;
+    h->act = c.use_mish ? ACT_MISH : ACT_GELU;
+    int rc = build_weight_table(h);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+void vitdet_destroy(vitdet_handle* h) { delete h; }
+
+int vitdet_tokens(const vitdet_handle* h) { return h ? h->T : 0; }
+int vitdet_patch_dim(const vitdet_handle* h) { return h ? h->P : 0; }
+int64_t vitdet_count_params(const vitdet_handle* h) {
+    if (!h) return 0;
+    int64_t n = 0;
+    for (const WeightSlot& s : h->slots) n += s.count;
+    return n;
+}
+
+int vitdet_num_weights(const vitdet_handle* h) { return h ? static_cast<int>(h->slots.size()) : 0; }
+
+int vitdet_weight_info(const vitdet_handle* h, int index, char* name, int cap, int* ndim, int64_t shape[4]) {
+    if (!h || index < 0 || index >= static_cast<int>(h->slots.size())) return fail(VITDET_E_INVALID, "weight_info: bad index %d", index);
+    const WeightSlot& s = h->slots[index];
+    if (name && cap > 0) { strncpy(name, s.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (ndim) *ndim = s.ndim;
+    if (shape) for (int i = 0; i < 4; ++i) shape[i] = i < s.ndim ? s.shape[i] : 1;
+    return 0;
+}
+
+int vitdet_set_weight(vitdet_handle* h, const char* name_in, const float* data, int ndim, const int64_t* shape) {
+    if (!h || !name_in || !data) return fail(VITDET_E_INVALID, "set_weight: null argument");
+    std::string name(name_in);
+    if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
+    auto it = h->slot_index.find(name);
+    if (it == h->slot_index.end()) return fail(VITDET_E_NOT_FOUND, "set_weight: unknown weight '%s'", name.c_str());
+    WeightSlot& s = h->slots[it->second];
+    if (ndim != s.ndim) return fail(VITDET_E_SHAPE, "set_weight('%s'): rank %d, expected %d", name.c_str(), ndim, s.ndim);
+    for (int i = 0; i < ndim; ++i)
+        if (shape[i] != s.shape[i]) return fail(VITDET_E_SHAPE, "set_weight('%s'): dim %d is %lld, expected %lld", name.c_str(), i, (long long)shape[i], (long long)s.shape[i]);
+    RC_TRY(h->stage.ensure(static_cast<size_t>(s.count) * 4));
+    CU_TRY(cudaMemcpy(h->stage.p, data, static_cast<size_t>(s.count) * 4, cudaMemcpyHostToDevice));
+    const float* src = h->stage.as<float>();
+    switch (s.kind) {
+        case WeightSlot::DENSE_KERNEL:
+            pack_dense_kernel<<<blocks_for(s.count), 256>>>(src, s.K, s.N, s.gn, s.pn, s.row_off, s.gk, s.pk,
+                                                            s.dense->w16.as<__nv_bfloat16>(), s.dense->ld16,
+                                                            s.dense->w32.as<float>(), s.dense->ld32);
+            break;
+        case WeightSlot::DENSE_BIAS:
+            pack_vec_kernel<<<blocks_for(s.N), 256>>>(src, s.N, s.gn, s.pn, s.row_off, s.dense->bias.as<float>());
+            break;
+        case WeightSlot::VEC:
+            if (s.vec_transpose)   // keep as f32 [N, K]
+                pack_dense_kernel<<<blocks_for(s.count), 256>>>(src, s.K, s.N, s.N, s.N, 0, s.K, s.K, nullptr, 0, s.vec_dst, s.K);
+            else
+                CU_TRY(cudaMemcpy(s.vec_dst, src, static_cast<size_t>(s.count) * 4, cudaMemcpyDeviceToDevice));
+            break;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaDeviceSynchronize());
+    s.master.assign(data, data + s.count);
+    s.set = true;
+    return 0;
+}
+
+int vitdet_get_weight(const vitdet_handle* h, const char* name_in, float* data, int64_t capacity) {
+    if (!h || !name_in || !data) return fail(VITDET_E_INVALID, "get_weight: null argument");
+    std::string name(name_in);
+    if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
+    auto it = h->slot_index.find(name);
+    if (it == h->slot_index.end()) return fail(VITDET_E_NOT_FOUND, "get_weight: unknown weight '%s'", name.c_str());
+    const WeightSlot& s = h->slots[it->second];
+    if (!s.set) return fail(VITDET_E_UNSET, "get_weight('%s'): weight has not been set", name.c_str());
+    if (capacity < s.count) return fail(VITDET_E_SHAPE, "get_weight('%s'): capacity %lld < %lld", name.c_str(), (long long)capacity, (long long)s.count);
+    memcpy(data, s.master.data(), static_cast<size_t>(s.count) * 4);
+    return 0;
+}
+
+int vitdet_profile_enable(vitdet_handle* h, uint32_t category_mask) {
+    if (!h) return fail(VITDET_E_INVALID, "profile_enable: null handle");
+    h->prof_mask = category_mask;
+    return 0;
+}
+
+int vitdet_profile_num_categories(const vitdet_handle* h) {
+    return h ? PC_MLP0 + h->cfg.mlp_quantities : 0;
+}
+
+const char* vitdet_profile_category_name(int category) { return prof_cat_name(category); }
+
+int vitdet_profile_read(vitdet_handle* h, int category, double* total_ms, int64_t* launches, int reset) {
+    if (!h || category < 0 || category >= 32) return fail(VITDET_E_INVALID, "profile_read: bad arguments");
+    RC_TRY(prof_collect(h));
+    if (total_ms) *total_ms = h->prof_ms[category];
+    if (launches) *launches = h->prof_n[category];
+    if (reset) { h->prof_ms[category] = 0; h->prof_n[category] = 0; }
+    return 0;
+}
+
+int64_t vitdet_launch_count(vitdet_handle* h, int reset) {
+    if (!h) return 0;
+    const long long n = h->launches;
+    if (reset) h->launches = 0;
+    return n;
+}
+
+int vitdet_set_chunk(vitdet_handle* h, int n) {
+    if (!h || n <= 0) return fail(VITDET_E_INVALID, "set_chunk: bad argument");
+    h->chunk = n;
+    return 0;
+}
+
+size_t vitdet_workspace_bytes(const vitdet_handle* h, int B, int mode) {
+    if (!h || B <= 0) return 0;
+    return workspace_bytes(h, B, mode);
+}
+
+int vitdet_forward(vitdet_handle* h, const float* images_dev, int B, float* logits_dev, int mode, void* stream) {
+    if (!logits_dev) return fail(VITDET_E_INVALID, "forward: logits_dev is null");
+    return forward_impl(h, images_dev, B, mode, logits_dev, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int vitdet_forward_decode(vitdet_handle* h, const float* images_dev, int B, int mode, const vitdet_decode_params* params,
+                          float* logits_dev, const vitdet_detections* out, void* stream) {
+    if (!params || !out) return fail(VITDET_E_INVALID, "forward_decode: null params / out");
+    return forward_impl(h, images_dev, B, mode, logits_dev, params, out, static_cast<cudaStream_t>(stream));
+}
+
+int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* p, const vitdet_detections* out, void* stream) {
+    if (!logits_dev || !p || !out || R < 0) return fail(VITDET_E_INVALID, "decode: bad arguments");
+    if (R == 0) return 0;
+    DecodeParams dp;
+    dp.obj_thr = p->objectness_threshold; dp.cls_thr = p->classification_threshold; dp.strict = p->strict;
+    dp.img_h = p->image_h; dp.img_w = p->image_w; dp.classes = p->classes;
+    dp.apply_transform = p->use_transform_predictions ? 1 : 0;
+    DecodeOut o;
+    o.decoded = out->decoded; o.class_id = out->class_id; o.class_conf = out->class_conf; o.keep = out->keep; o.corners = out->corners;
+    CU_TRY(decode_launch(logits_dev, R, dp, o, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_params* p, const vitdet_detections* out_host) {
+    if (!logits_host || !p || !out_host || R < 0) return fail(VITDET_E_INVALID, "decode_host: bad arguments");
+    if (R == 0) return 0;
+    const size_t r = static_cast<size_t>(R);
+    const size_t o_dec = a256(r * 24), o_id = o_dec + a256(r * 24), o_cc = o_id + a256(r * 4), o_cor = o_cc + a256(r * 4),
+                 o_keep = o_cor + a256(r * 16), total = o_keep + a256(r);
+    DevBuf buf;
+    RC_TRY(buf.ensure(total));
+    char* b = buf.as<char>();
+    CU_TRY(cudaMemcpy(b, logits_host, r * 24, cudaMemcpyHostToDevice));
+    vitdet_detections d;
+    d.decoded = reinterpret_cast<float*>(b + o_dec);
+    d.class_id = reinterpret_cast<int32_t*>(b + o_id);
+    d.class_conf = reinterpret_cast<float*>(b + o_cc);
+    d.corners = reinterpret_cast<int32_t*>(b + o_cor);
+    d.keep = reinterpret_cast<uint8_t*>(b + o_keep);
+    RC_TRY(vitdet_decode(reinterpret_cast<const float*>(b), R, p, &d, nullptr));
+    CU_TRY(cudaDeviceSynchronize());
+    if (out_host->decoded) CU_TRY(cudaMemcpy(out_host->decoded, d.decoded, r * 24, cudaMemcpyDeviceToHost));
+    if (out_host->class_id) CU_TRY(cudaMemcpy(out_host->class_id, d.class_id, r * 4, cudaMemcpyDeviceToHost));
+    if (out_host->class_conf) CU_TRY(cudaMemcpy(out_host->class_conf, d.class_conf, r * 4, cudaMemcpyDeviceToHost));
+    if (out_host->corners) CU_TRY(cudaMemcpy(out_host->corners, d.corners, r * 16, cudaMemcpyDeviceToHost));
+    if (out_host->keep) CU_TRY(cudaMemcpy(out_host->keep, d.keep, r, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int mode, const vitdet_decode_params* params,
+                        float* logits_host, const vitdet_detections* out_host, void* stream) {
+    if (!h || !images_host || B <= 0 || !params) return fail(VITDET_E_INVALID, "predict_host: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = static_cast<size_t>(B) * h->cfg.image_h * h->cfg.image_w * 3 * 4;
+    const size_t R = static_cast<size_t>(B) * h->S;
+    // output record block: logits 24 | decoded 24 | class_id 4 | class_conf 4 | corners 16 | keep 1  bytes per row
+    const size_t o_logits = 0, o_dec = a256(R * 24), o_id = o_dec + a256(R * 24), o_cc = o_id + a256(R * 4),
+                 o_cor = o_cc + a256(R * 4), o_keep = o_cor + a256(R * 16), out_bytes = o_keep + a256(R);
+    if (h->pin_in_bytes < in_bytes) {
+        if (h->pin_in) cudaFreeHost(h->pin_in);
+        h->pin_in = nullptr; h->pin_in_bytes = 0;
+        CU_TRY(cudaHostAlloc(&h->pin_in, in_bytes, cudaHostAllocDefault));
+        h->pin_in_bytes = in_bytes;
+    }
+    if (h->pin_out_bytes < out_bytes) {
+        if (h->pin_out) cudaFreeHost(h->pin_out);
+        h->pin_out = nullptr; h->pin_out_bytes = 0;
+        CU_TRY(cudaHostAlloc(&h->pin_out, out_bytes, cudaHostAllocDefault));
+        h->pin_out_bytes = out_bytes;
+    }
+    RC_TRY(h->dev_in.ensure(in_bytes));
+    RC_TRY(h->dev_out.ensure(out_bytes));
+    // If the caller's buffer is already page-locked, copy straight from it; otherwise stage through
+    // the handle's pinned buffer (a pageable cudaMemcpyAsync would do the same staging, serially).
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const void* src = images_host;
+    if (!pinned) { memcpy(h->pin_in, images_host, in_bytes); src = h->pin_in; }
+    CU_TRY(cudaMemcpyAsync(h->dev_in.p, src, in_bytes, cudaMemcpyHostToDevice, st));
+    char* dbase = h->dev_out.as<char>();
+    vitdet_detections d;
+    d.decoded = reinterpret_cast<float*>(dbase + o_dec);
+    d.class_id = reinterpret_cast<int32_t*>(dbase + o_id);
+    d.class_conf = reinterpret_cast<float*>(dbase + o_cc);
+    d.corners = reinterpret_cast<int32_t*>(dbase + o_cor);
+    d.keep = reinterpret_cast<uint8_t*>(dbase + o_keep);
+    RC_TRY(forward_impl(h, h->dev_in.as<float>(), B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st));
+    CU_TRY(cudaMemcpyAsync(h->pin_out, dbase, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const char* pb = static_cast<const char*>(h->pin_out);
+    if (logits_host) memcpy(logits_host, pb + o_logits, R * 24);
+    if (out_host) {
+        if (out_host->decoded) memcpy(out_host->decoded, pb + o_dec, R * 24);
+        if (out_host->class_id) memcpy(out_host->class_id, pb + o_id, R * 4);
+        if (out_host->class_conf) memcpy(out_host->class_conf, pb + o_cc, R * 4);
+        if (out_host->corners) memcpy(out_host->corners, pb + o_cor, R * 16);
+        if (out_host->keep) memcpy(out_host->keep, pb + o_keep, R);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator-level entry points
+// ------------------------------------------------------------------------------------------------
+int vitdet_op_dense(const float* A, const float* kernel, const float* bias, const float* resid, float* out, int M, int K,
+                    int N, int act, int mode, void* stream) {
+    if (!A || !kernel || !out || M <= 0 || K <= 0 || N <= 0) return fail(VITDET_E_INVALID, "op_dense: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DenseW w;
+    RC_TRY(w.alloc(N, K));
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16,
+                                                                               w.w32.as<float>(), w.ld32);
+    if (bias) CU_TRY(cudaMemcpyAsync(w.bias.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, st));
+    const int N4 = round_up(N, 4);
+    DevBuf a_buf, o_buf, r_buf;
+    RC_TRY(o_buf.ensure(static_cast<size_t>(M) * N4 * 4));
+    const float* rp = nullptr;
+    if (resid) {
+        RC_TRY(r_buf.ensure(static_cast<size_t>(M) * N4 * 4));
+        pad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * N4), 256, 0, st>>>(resid, M, N, N, r_buf.as<float>(), N4);
+        rp = r_buf.as<float>();
+    }
+    int rc = 0;
+    if (mode == VITDET_MODE_BF16) {
+        const int K8 = round_up(K, 8);
+        RC_TRY(a_buf.ensure(static_cast<size_t>(M) * K8 * 2));
+        f32_to_bf16_kernel<<<blocks_for(static_cast<long long>(M) * K8), 256, 0, st>>>(A, M, K, K, a_buf.as<__nv_bfloat16>(), K8);
+        DenseCall c{a_buf.p, K8, &w, nullptr, 1, rp, N4, o_buf.p, N4, 1, act, M};
+        TcGemmPlan plan;
+        GemmDesc g = make_desc(c, VITDET_MODE_BF16);
+        rc = tc_gemm_make_plan(&plan, g, sms);
+        if (rc) return fail(VITDET_E_INVALID, "op_dense: tc_gemm_make_plan failed: %d", rc);
+        RC_TRY(launch_tc(plan, o_buf.p, rp, st));
+    } else {
+        const int K4 = round_up(K, 4);
+        RC_TRY(a_buf.ensure(static_cast<size_t>(M) * K4 * 4));
+        pad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * K4), 256, 0, st>>>(A, M, K, K, a_buf.as<float>(), K4);
+        DenseCall c{a_buf.p, K4, &w, nullptr, 1, rp, N4, o_buf.p, N4, 1, act, M};
+        RC_TRY(launch_simt(c, st));
+    }
+    unpad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * N), 256, 0, st>>>(o_buf.as<float>(), M, N, N4, out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vitdet_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int D, float eps, void* stream) {
+    if (!x || !gamma || !beta || !y || M <= 0 || D <= 0) return fail(VITDET_E_INVALID, "op_layernorm: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D4 = round_up(D, 4);
+    if (D4 == D) {
+        CU_TRY(layernorm_launch(x, D, gamma, beta, M, D, eps, y, D, 1, st));
+        return 0;
+    }
+    DevBuf xb, yb;
+    RC_TRY(xb.ensure(static_cast<size_t>(M) * D4 * 4));
+    RC_TRY(yb.ensure(static_cast<size_t>(M) * D4 * 4));
+    pad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * D4), 256, 0, st>>>(x, M, D, D, xb.as<float>(), D4);
+    CU_TRY(layernorm_launch(xb.as<float>(), D4, gamma, beta, M, D, eps, yb.p, D4, 1, st));
+    unpad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * D), 256, 0, st>>>(yb.as<float>(), M, D, D4, y);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vitdet_op_attention(const float* q, const float* k, const float* v, float* out, int B, int T, int H, int d, int mode,
+                        void* stream) {
+    if (!q || !k || !v || !out || B <= 0 || T <= 0 || H <= 0 || d <= 0 || d > kHeadPitch)
+        return fail(VITDET_E_INVALID, "op_attention: bad arguments (key_dim must be <= %d)", kHeadPitch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int hp = kHeadPitch;
+    const long long rows = static_cast<long long>(B) * T;
+    const int es = mode == VITDET_MODE_BF16 ? 2 : 4;
+    DevBuf qkv, ctx;
+    RC_TRY(qkv.ensure(static_cast<size_t>(rows) * 3 * H * hp * es));
+    RC_TRY(ctx.ensure(static_cast<size_t>(rows) * H * hp * es));
+    AttnDesc ad;
+    ad.qkv = qkv.p; ad.ldq = 3 * H * hp; ad.ctx = ctx.p; ad.ldo = H * hp;
+    ad.B = B; ad.T = T; ad.H = H; ad.d = d; ad.hp = hp; ad.scale = 1.f / sqrtf(static_cast<float>(d));
+    if (mode == VITDET_MODE_BF16) {
+        pack_qkv_kernel<__nv_bfloat16><<<blocks_for(rows * 3 * H * hp), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<__nv_bfloat16>());
+        AttnPlan plan;
+        int rc = attn_bf16_make_plan(&plan, ad);
+        if (rc) return fail(VITDET_E_INVALID, "op_attention: attn_bf16_make_plan failed: %d", rc);
+        CU_TRY(attn_bf16_launch(plan, st));
+        unpack_ctx_kernel<__nv_bfloat16><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<__nv_bfloat16>(), rows, H, d, hp, out);
+    } else {
+        pack_qkv_kernel<float><<<blocks_for(rows * 3 * H * hp), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<float>());
+        CU_TRY(attn_f32_launch(ad, st));
+        unpack_ctx_kernel<float><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<float>(), rows, H, d, hp, out);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vitdet_op_patchify(const float* images, int B, int H, int W, int p, float* patches, void* stream) {
+    if (!images || !patches || B <= 0 || H <= 0 || W <= 0 || p <= 0) return fail(VITDET_E_INVALID, "op_patchify: bad arguments");
+    CU_TRY(patchify_launch(images, B, H, W, p, patches, 3 * p * p, 1, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+}  // extern "C"

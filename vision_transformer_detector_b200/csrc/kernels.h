@@ -1,0 +1,115 @@
+// Internal (C++) declarations of the kernel launchers.  The public boundary is include/vitdet_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vitdet {
+
+// ------------------------------------------------------------------------------------------------
+// Dense layer:  out[M, ldc] = epilogue( A[M,K] (lda) * W[N,K]^T (ldw) )
+//   epilogue(acc)[m,n] = act(acc + bias[n] + pos[m % pos_period]) + resid[m,n]
+// (the order matches the reference graph: Dense -> activation -> keras.layers.add, det.py:388-412,
+//  and Dense -> add(position) for the patch embedding, det.py:297-307).
+// Columns [N, round_up(N, vec)) of `out` are written as zero, vec = 8 (bf16) or 4 (f32).
+// ------------------------------------------------------------------------------------------------
+struct GemmDesc {
+    const void* A = nullptr;   // bf16 (tensor-core path) or f32 (SIMT path), row-major, K contiguous
+    int lda = 0;
+    const void* W = nullptr;   // same element type as A; row n = output unit n, K contiguous
+    int ldw = 0;
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;
+    const float* pos = nullptr;
+    int pos_period = 1;
+    const float* resid = nullptr;   // f32, only with out_f32; may alias `out`
+    int ldr = 0;
+    void* out = nullptr;
+    int ldc = 0;
+    int out_f32 = 0;
+    int act = 0;               // vitdet::Act
+    int block_n = 0;           // 0 = choose
+};
+
+struct TcGemmPlan {
+    CUtensorMap tmA, tmB;
+    GemmDesc desc;
+    int block_n = 0;
+    int num_stages = 0;
+    int n_tiles = 0;
+    int num_tiles = 0;
+    int grid = 0;
+    size_t smem_bytes = 0;
+};
+
+int choose_block_n(int N);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
+int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms);
+cudaError_t tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
+
+// f32 CUDA-core GEMM with the same epilogue (the fp32 parity mode); A, W, out are f32.
+// Requires lda, ldw multiples of 4 and zero padding of A and W in columns [K, round_up(K,4)).
+cudaError_t simt_gemm_launch(const GemmDesc& d, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Attention.  qkv: [B*T, ldq] with q of head h at columns [h*hp, h*hp+d), k at [(H+h)*hp, ...),
+// v at [(2H+h)*hp, ...); ctx: [B*T, H*hp] (columns d..hp-1 of every head written as zero).
+// ------------------------------------------------------------------------------------------------
+struct AttnDesc {
+    const void* qkv = nullptr;
+    int ldq = 0;
+    void* ctx = nullptr;
+    int ldo = 0;
+    int B = 0, T = 0, H = 0, d = 0, hp = 0;
+    float scale = 1.f;          // 1/sqrt(key_dim), applied to q·k (Keras scales q after its bias)
+};
+struct AttnPlan {
+    CUtensorMap tmQKV;
+    AttnDesc desc;
+};
+int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d);
+cudaError_t attn_bf16_launch(const AttnPlan& plan, cudaStream_t stream);
+cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Memory-bound row kernels
+// ------------------------------------------------------------------------------------------------
+// tf.image.extract_patches(sizes=strides=p, padding='SAME') + Reshape (det.py:195-197, 279-280).
+// images f32 NHWC [B,H,W,3] -> patches [B*gh*gw, ldp] (element (r*p + c)*3 + ch), zero padded.
+cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp,
+                            int out_f32, cudaStream_t stream);
+
+// keras LayerNormalization(axis=-1), eps=1e-3, biased variance (det.py:353-357, 375-379).
+cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D,
+                             float eps, void* y, int ldy, int out_f32, cudaStream_t stream);
+
+// mlp_head first stage (det.py:454-463): Dense(D -> S) on every token, stored compactly as
+// [B, T*S] so that the reference's Reshape((S,-1)) is the row-major view [B*S, T].
+cudaError_t head_slots_launch(const float* x, int ldx, const float* w /*[S, D] f32*/, const float* bias,
+                              int M, int D, int S, void* out, int out_f32, cudaStream_t stream);
+
+// Final Dense(U -> 6) 'MLP_Head_no_Sigmoid' (det.py:489-493) fused with transform_predictions
+// (det.py:586-647) and the 0.5/0.5 thresholds (det.py:2257-2283 / 1359-1384).
+struct DecodeParams {
+    float obj_thr = 0.5f, cls_thr = 0.5f;
+    int strict = 1;             // 1: keep iff score >  thr (metric copy); 0: keep iff score >= thr (visualise copy)
+    float img_h = 608.f, img_w = 608.f;
+    int classes = 80;
+    int apply_transform = 1;    // 0: rows are already transform_predictions output (det.py:1340-1341)
+};
+struct DecodeOut {
+    float* logits = nullptr;    // [R, 6] raw (optional when decoding given logits)
+    float* decoded = nullptr;   // [R, 6] conf, class in [0, classes-1], cx, cy, h, w (pixels)
+    int32_t* class_id = nullptr;  // [R] round-half-even(class)
+    float* class_conf = nullptr;  // [R] (0.5 - |class - id|) / 0.5
+    uint8_t* keep = nullptr;    // [R]
+    int32_t* corners = nullptr; // [R, 4] x0, y0, x1, y1 (int truncation then clip; det.py:2300-2325), optional
+};
+cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w /*[6, U] f32*/, const float* bias,
+                             int R, int U, const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream);
+cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,
+                          cudaStream_t stream);
+
+}  // namespace vitdet

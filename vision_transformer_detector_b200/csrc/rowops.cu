@@ -1,0 +1,341 @@
+// Memory-bound kernels of the hot path: patch extraction, LayerNorm, the head's per-token slot
+// projection, and the fused head tail (Dense(U->6) + sigmoid + clip + scale + thresholds).
+// All of them are HBM/L2 streaming kernels: coalesced 16-byte accesses where the layout allows it,
+// warp-shuffle reductions, no shared-memory staging (there is no reuse to exploit).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vitdet {
+
+namespace {
+
+template <typename T> struct OutT;
+template <> struct OutT<float> {
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <> struct OutT<__nv_bfloat16> {
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ void st4(__nv_bfloat16* p, float a, float b, float c, float d) {
+        uint2 o;
+        o.x = pack_bf16x2(a, b);
+        o.y = pack_bf16x2(c, d);
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1 patchify.  tf.image.extract_patches(sizes=strides=[1,p,p,1], rates=1, padding='SAME')
+// (det.py:195-197) followed by Reshape((-1, 3p^2)) (det.py:279-280):
+//   grid = ceil(H/p) x ceil(W/p); pad_total = grid*p - size, pad_before = pad_total / 2, zeros;
+//   patch vector element (r*p + c)*3 + ch; tokens row-major over the grid.
+// One block per (image, padded image row): reads one contiguous image row, writes gw runs of 3p
+// elements.  Blocks with r == 0 also clear the pad columns [3p^2, ldp) of their gw tokens.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, int H, int W, int p, int gh, int gw, int pad_top,
+                int pad_left, T* __restrict__ out, int ldp) {
+    const int yy = blockIdx.x;          // padded row index in [0, gh*p)
+    const int b = blockIdx.y;
+    const int py = yy / p, r = yy - py * p;
+    const int y = yy - pad_top;
+    const int run = 3 * p;              // contiguous elements per (token, r)
+    const int row_elems = gw * run;
+    const bool y_ok = (y >= 0) && (y < H);
+    const float* src = img + (static_cast<size_t>(b) * H + (y_ok ? y : 0)) * W * 3;
+    const size_t tok0 = (static_cast<size_t>(b) * gh + py) * gw;
+    const int P = run * p;
+    for (int e = threadIdx.x; e < row_elems; e += blockDim.x) {
+        const int px = e / run;
+        const int within = e - px * run;
+        const int x3 = e - 3 * pad_left;
+        float v = 0.f;
+        if (y_ok && x3 >= 0 && x3 < 3 * W) v = __ldg(src + x3);
+        OutT<T>::st(out + (tok0 + px) * ldp + r * run + within, v);
+    }
+    if (r == 0 && ldp > P) {
+        const int padw = ldp - P;
+        for (int e = threadIdx.x; e < gw * padw; e += blockDim.x) {
+            const int px = e / padw;
+            OutT<T>::st(out + (tok0 + px) * ldp + P + (e - px * padw), 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 LayerNorm over the last axis, eps inside the rsqrt, biased variance, f32 statistics
+// (keras.layers.LayerNormalization defaults; det.py:353-357, 375-379).
+// LPR lanes cooperate on one row (8 for the 28-wide default stream: four rows per warp, each lane
+// one float4; 32 for wide streams).  The row is held in registers between the two reduction
+// passes (CH float4 per lane), so x is read exactly once.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int CH, typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int M, int D, float eps, T* __restrict__ y, int ldy) {
+    constexpr int ROWS_PER_BLOCK = 256 / LPR;
+    const int sub = threadIdx.x % LPR;
+    const int row = blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / LPR;
+    const bool row_ok = row < M;
+    const float* xr = x + static_cast<size_t>(row_ok ? row : 0) * ldx;
+
+    float4 v[CH];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int e = 4 * (sub + i * LPR);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && e < D) {
+            if (e + 4 <= D) {
+                v[i] = *reinterpret_cast<const float4*>(xr + e);
+            } else {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < 4 && e + j < D; ++j) t[j] = xr[e + j];
+                v[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(D);
+
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int e = 4 * (sub + i * LPR);
+        const float d0 = (e + 0 < D) ? v[i].x - mean : 0.f;
+        const float d1 = (e + 1 < D) ? v[i].y - mean : 0.f;
+        const float d2 = (e + 2 < D) ? v[i].z - mean : 0.f;
+        const float d3 = (e + 3 < D) ? v[i].w - mean : 0.f;
+        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
+
+    if (!row_ok) return;
+    T* yr = y + static_cast<size_t>(row) * ldy;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int e = 4 * (sub + i * LPR);
+        if (e < ldy) {       // pad columns [D, ldy) are written as zero
+            float o[4];
+            const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[j] = 0.f;
+                if (e + j < D) o[j] = (xv[j] - mean) * rstd * __ldg(gamma + e + j) + __ldg(beta + e + j);
+            }
+            OutT<T>::st4(yr + e, o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mlp_head first stage (det.py:454-463).  One thread per (token, slot); the output is the compact
+// row-major (M, S) matrix, whose flat buffer IS the reference's Reshape((S, -1)) result per image.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                  const float* __restrict__ bias, long long total, int D, int S, T* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long m = idx / S;
+    const int s = static_cast<int>(idx - m * S);
+    const float* xr = x + m * ldx;
+    const float* wr = w + static_cast<size_t>(s) * D;
+    float acc = 0.f;
+    int d = 0;
+    if ((D & 3) == 0) {
+        for (; d < D; d += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + d);
+            const float4 c = __ldg(reinterpret_cast<const float4*>(wr + d));
+            acc = fmaf(a.x, c.x, acc);
+            acc = fmaf(a.y, c.y, acc);
+            acc = fmaf(a.z, c.z, acc);
+            acc = fmaf(a.w, c.w, acc);
+        }
+    }
+    for (; d < D; ++d) acc = fmaf(xr[d], __ldg(wr + d), acc);
+    OutT<T>::st(out + idx, acc + __ldg(bias + s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode of one slot: transform_predictions (det.py:619-645) + thresholds + corner boxes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.f / (1.f + expf(-x)); }
+
+// tf.clip_by_value(x, 0, 1) = minimum(maximum(x, 0), 1); TF's maximum/minimum propagate NaN.
+__device__ __forceinline__ float clip01_nan(float x) { return (x != x) ? x : fminf(fmaxf(x, 0.f), 1.f); }
+
+__device__ __forceinline__ int clip_int(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ void decode_slot(const float (&l)[6], long long r, const DecodeParams& dp,
+                                            const DecodeOut& o) {
+    float dec[6];
+    if (dp.apply_transform) {
+        float s[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) s[j] = sigmoid_f32(l[j]);
+#pragma unroll
+        for (int j = 2; j < 6; ++j) s[j] = clip01_nan(s[j]);
+        dec[0] = s[0];
+        dec[1] = s[1] * static_cast<float>(dp.classes - 1);
+        dec[2] = s[2] * dp.img_w;   // center_x   (det.py:637)
+        dec[3] = s[3] * dp.img_h;   // center_y   (det.py:638)
+        dec[4] = s[4] * dp.img_h;   // bbox_height(det.py:639)
+        dec[5] = s[5] * dp.img_w;   // bbox_width (det.py:640)
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dec[j] = l[j];
+    }
+    const float id = rintf(dec[1]);                 // tf.round / np.round: half to even
+    const float err = fabsf(dec[1] - id);
+    const float cc = (0.5f - err) / 0.5f;           // det.py:1376, 2279
+    bool keep;
+    if (dp.strict) keep = (dec[0] > dp.obj_thr) && (cc > dp.cls_thr);        // det.py:1381-1384
+    else keep = !(dec[0] < dp.obj_thr) && !(cc < dp.cls_thr);               // det.py:2264, 2282
+    if (o.logits) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o.logits[r * 6 + j] = l[j];
+    }
+    if (o.decoded) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o.decoded[r * 6 + j] = dec[j];
+    }
+    if (o.class_id) o.class_id[r] = static_cast<int32_t>(id);
+    if (o.class_conf) o.class_conf[r] = cc;
+    if (o.keep) o.keep[r] = keep ? 1 : 0;
+    if (o.corners) {
+        // det.py:2300-2325: int() truncation toward zero, then clip to the image.
+        const int iw = static_cast<int>(dp.img_w), ih = static_cast<int>(dp.img_h);
+        o.corners[r * 4 + 0] = clip_int(static_cast<int>(dec[2] - dec[5] / 2.f), 0, iw);
+        o.corners[r * 4 + 1] = clip_int(static_cast<int>(dec[3] - dec[4] / 2.f), 0, ih);
+        o.corners[r * 4 + 2] = clip_int(static_cast<int>(dec[2] + dec[5] / 2.f), 0, iw);
+        o.corners[r * 4 + 3] = clip_int(static_cast<int>(dec[3] + dec[4] / 2.f), 0, ih);
+    }
+}
+
+__device__ __forceinline__ float ld_as_f32(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_f32(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// K9: one warp per (image, slot) row: 6 dot products of length U, shuffle reduction, lane 0 decodes.
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_tail_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ w, const float* __restrict__ bias,
+                 int R, int U, DecodeParams dp, DecodeOut o) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= R) return;
+    const T* hr = h + static_cast<size_t>(warp) * ldh;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int u = lane; u < U; u += 32) {
+        const float a = ld_as_f32(hr + u);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[j] = fmaf(a, __ldg(w + j * U + u), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (lane == 0) {
+        float l[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) l[j] = acc[j] + __ldg(bias + j);
+        decode_slot(l, warp, dp, o);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+decode_kernel(const float* __restrict__ logits, int R, DecodeParams dp, DecodeOut o) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float l[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) l[j] = logits[static_cast<size_t>(r) * 6 + j];
+    DecodeOut o2 = o;
+    if (o2.logits == logits) o2.logits = nullptr;
+    decode_slot(l, r, dp, o2);
+}
+
+template <int LPR, typename T>
+cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b, int M, int D, float eps, T* y,
+                        int ldy, cudaStream_t st) {
+    const int rows_per_block = 256 / LPR;
+    const int grid = (M + rows_per_block - 1) / rows_per_block;
+    const int width = ldy > D ? ldy : D;
+    const int chunks = (width + 4 * LPR - 1) / (4 * LPR);
+    if (chunks <= 1) layernorm_kernel<LPR, 1, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 2) layernorm_kernel<LPR, 2, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 4) layernorm_kernel<LPR, 4, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 8) layernorm_kernel<LPR, 8, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 16) layernorm_kernel<LPR, 16, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
+    else return cudaErrorInvalidValue;   // embedding_dim > 2048 is outside what this build supports
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int out_f32,
+                            cudaStream_t stream) {
+    const int gh = (H + p - 1) / p, gw = (W + p - 1) / p;
+    const int pad_top = (gh * p - H) / 2, pad_left = (gw * p - W) / 2;
+    if (ldp < 3 * p * p) return cudaErrorInvalidValue;
+    dim3 grid(gh * p, B);
+    if (out_f32)
+        patchify_kernel<float><<<grid, 256, 0, stream>>>(images, H, W, p, gh, gw, pad_top, pad_left,
+                                                         static_cast<float*>(patches), ldp);
+    else
+        patchify_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(images, H, W, p, gh, gw, pad_top, pad_left,
+                                                                 static_cast<__nv_bfloat16*>(patches), ldp);
+    return cudaGetLastError();
+}
+
+cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D, float eps,
+                             void* y, int ldy, int out_f32, cudaStream_t stream) {
+    if ((ldx % 4) || (ldy % 4) || M <= 0 || D <= 0) return cudaErrorInvalidValue;
+    const int width = ldy > D ? ldy : D;
+    if (width <= 32) {
+        if (out_f32) return ln_dispatch<8, float>(x, ldx, gamma, beta, M, D, eps, static_cast<float*>(y), ldy, stream);
+        return ln_dispatch<8, __nv_bfloat16>(x, ldx, gamma, beta, M, D, eps, static_cast<__nv_bfloat16*>(y), ldy, stream);
+    }
+    if (out_f32) return ln_dispatch<32, float>(x, ldx, gamma, beta, M, D, eps, static_cast<float*>(y), ldy, stream);
+    return ln_dispatch<32, __nv_bfloat16>(x, ldx, gamma, beta, M, D, eps, static_cast<__nv_bfloat16*>(y), ldy, stream);
+}
+
+cudaError_t head_slots_launch(const float* x, int ldx, const float* w, const float* bias, int M, int D, int S,
+                              void* out, int out_f32, cudaStream_t stream) {
+    const long long total = static_cast<long long>(M) * S;
+    const int grid = static_cast<int>((total + 255) / 256);
+    if (out_f32)
+        head_slots_kernel<float><<<grid, 256, 0, stream>>>(x, ldx, w, bias, total, D, S, static_cast<float*>(out));
+    else
+        head_slots_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, ldx, w, bias, total, D, S,
+                                                                   static_cast<__nv_bfloat16*>(out));
+    return cudaGetLastError();
+}
+
+cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w, const float* bias, int R, int U,
+                             const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream) {
+    const int grid = (R * 32 + 255) / 256;
+    if (in_f32)
+        head_tail_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(h), ldh, w, bias, R, U, dp, out);
+    else
+        head_tail_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), ldh, w, bias,
+                                                                  R, U, dp, out);
+    return cudaGetLastError();
+}
+
+cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,
+                          cudaStream_t stream) {
+    decode_kernel<<<(R + 255) / 256, 256, 0, stream>>>(logits, R, dp, out);
+    return cudaGetLastError();
+}
+
+}  // namespace vitdet
