@@ -33,6 +33,8 @@ constexpr int kStageBytesA = kBM * kBK * 2;   // 16 KiB
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
+constexpr int kRingBytes = 200 * 1024;            // budget of the A/B stage ring
+constexpr int kMaxDynSmem = kRingBytes + 1024;    // + alignment slack; static smem (~2.2 KB) must also fit in 227 KB
 
 struct TcGemmArgs {
     int M, N, K;
@@ -271,7 +273,7 @@ cudaError_t launch_variant(const TcGemmPlan& plan, const TcGemmArgs& a, cudaStre
     auto kern = gemm_tc_kernel<ACT, OUT_F32>;
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -325,7 +327,7 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     plan->desc = d;
     plan->block_n = bn;
     const int stage = kStageBytesA + bn * kBK * 2;
-    int stages = (200 * 1024) / stage;
+    int stages = kRingBytes / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     plan->num_stages = stages;
     plan->smem_bytes = static_cast<size_t>(stages) * stage + 1024;

@@ -37,20 +37,25 @@ def glorot_uniform(rng: np.random.Generator, shape) -> np.ndarray:
 def init_weight(rng: np.random.Generator, name: str, shape, *, spread: bool = False) -> np.ndarray:
     """Initial value of the Keras variable `name` (no ':0' suffix) of the given shape.
 
-    spread=True gives the "set B" of SURVEY §8(d): kernels x3 and biases U(-0.5, 0.5), so that the
-    logits leave the sigmoid ~ 0.5 knife-edge of the default initialisation."""
+    spread=True gives the "set B" used by the parity tests and the bench: the Keras-default kernels,
+    but non-trivial biases U(-0.1, 0.1), LayerNorm gamma U(0.5, 1.5) / beta U(-0.2, 0.2), and the last
+    Dense ('MLP_Head_no_Sigmoid') scaled x25 with bias U(-1, 1), so that every parameter kind takes part
+    in the arithmetic and the logits leave the sigmoid ~ 0.5 knife-edge that the default initialisation
+    sits on (|logit| ~ 0.05 there) without saturating."""
     leaf = name.rsplit("/", 1)[-1]
+    last = name.startswith("MLP_Head_no_Sigmoid/")
     if leaf == "kernel":
         w = glorot_uniform(rng, shape)
-        return (w * 3.0).astype(np.float32) if spread else w
+        return (w * 25.0).astype(np.float32) if (spread and last) else w
     if leaf == "bias":
         if spread:
-            return rng.uniform(-0.5, 0.5, size=shape).astype(np.float32)
+            lim = 1.0 if last else 0.1
+            return rng.uniform(-lim, lim, size=shape).astype(np.float32)
         return np.zeros(shape, np.float32)
     if leaf == "gamma":
-        return np.ones(shape, np.float32)
+        return rng.uniform(0.5, 1.5, size=shape).astype(np.float32) if spread else np.ones(shape, np.float32)
     if leaf == "beta":
-        return np.zeros(shape, np.float32)
+        return rng.uniform(-0.2, 0.2, size=shape).astype(np.float32) if spread else np.zeros(shape, np.float32)
     if leaf == "embeddings":
         return rng.uniform(-0.05, 0.05, size=shape).astype(np.float32)
     raise ValueError(f"unknown variable kind: {name}")
