@@ -186,6 +186,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import vision_transformer_detector_b200 as vd
+    from vision_transformer_detector_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,16 +218,13 @@ def run_ours(args):
     x_dev = torch.rand((B, *cfg.input_shape), generator=g, device=dev, dtype=torch.float32) * 2 - 1
     img_size = cfg.input_shape[:2]
     rec_bytes = S * (24 + 4 + 4 + 1 + 16)      # decoded, class_id, class_conf, keep, corners per image
+    assert parallel.RECORD_WIDTH == 13
 
     def step():
         rec = model.detect(x_dev, image_size=img_size)
         if world > 1:
-            # the path's only exchange: fixed-size detection records of every rank, all-gathered
-            packed = torch.cat([rec.decoded.reshape(B * S, 6), rec.class_id.reshape(B * S, 1).to(torch.float32),
-                                rec.keep.reshape(B * S, 1).to(torch.float32)], dim=1)
-            out = torch.empty((world * B * S, 8), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(out, packed)
-            return out
+            # the path's only exchange: fixed-size detection records of every rank, all-gathered (NCCL)
+            return parallel.all_gather_records(parallel.pack_records(rec))
         return rec
 
     def barrier():
@@ -280,10 +278,7 @@ def run_ours(args):
         for _ in range(args.steps):
             rec = model.detect(x_np, image_size=img_size)     # vitdet_predict_host: synchronous, returns numpy records
             if world > 1:
-                packed = torch.from_numpy(np.concatenate([rec.decoded.reshape(B * S, 6), rec.class_id.reshape(B * S, 1).astype(np.float32),
-                                                          rec.keep.reshape(B * S, 1).astype(np.float32)], axis=1)).to(dev)
-                out = torch.empty((world * B * S, 8), dtype=torch.float32, device=dev)
-                dist.all_gather_into_tensor(out, packed)
+                parallel.all_gather_records(torch.from_numpy(parallel.pack_records(rec)).to(dev))
         e1.record()
         barrier()
         wall = time.perf_counter() - t0

@@ -1,0 +1,53 @@
+"""Data-parallel plumbing of the path: images are independent, so the batch is sharded across
+one process per GPU with no data-path collective; the only exchange is the all-gather of the fixed-size
+per-image detection records.  torch.distributed carries it (NCCL on GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+RECORD_WIDTH = 13          # decoded[6] | class_id | class_conf | keep | corners[4], all as float32 (ints are exact < 2^24)
+
+
+def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of `total` images for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_records(rec):
+    """DetectionRecords (torch tensors or numpy arrays, shapes (B,17,...)) -> float32 [B*17, 13]."""
+    if hasattr(rec.decoded, "is_cuda"):
+        import torch
+        B, S = rec.class_id.shape
+        f = torch.float32
+        return torch.cat([rec.decoded.reshape(B * S, 6), rec.class_id.reshape(B * S, 1).to(f),
+                          rec.class_conf.reshape(B * S, 1), rec.keep.reshape(B * S, 1).to(f),
+                          rec.corners.reshape(B * S, 4).to(f)], dim=1)
+    B, S = rec.class_id.shape
+    return np.concatenate([rec.decoded.reshape(B * S, 6), rec.class_id.reshape(B * S, 1).astype(np.float32),
+                           rec.class_conf.reshape(B * S, 1), rec.keep.reshape(B * S, 1).astype(np.float32),
+                           rec.corners.reshape(B * S, 4).astype(np.float32)], axis=1).astype(np.float32)
+
+
+def unpack_records(packed, slots: int = 17) -> dict:
+    """Inverse of pack_records on a gathered [N*17, 13] block -> dict of (N,17,...) arrays/tensors."""
+    n = packed.shape[0] // slots
+    if hasattr(packed, "is_cuda"):
+        import torch
+        return {"decoded": packed[:, 0:6].reshape(n, slots, 6), "class_id": packed[:, 6].to(torch.int32).reshape(n, slots),
+                "class_conf": packed[:, 7].reshape(n, slots), "keep": packed[:, 8].to(torch.uint8).reshape(n, slots),
+                "corners": packed[:, 9:13].to(torch.int32).reshape(n, slots, 4)}
+    return {"decoded": packed[:, 0:6].reshape(n, slots, 6), "class_id": packed[:, 6].astype(np.int32).reshape(n, slots),
+            "class_conf": packed[:, 7].reshape(n, slots), "keep": packed[:, 8].astype(np.uint8).reshape(n, slots),
+            "corners": packed[:, 9:13].astype(np.int32).reshape(n, slots, 4)}
+
+
+def all_gather_records(packed):
+    """All-gathers equally sized packed record blocks of every rank, in rank order (one collective)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous())
+    return out
