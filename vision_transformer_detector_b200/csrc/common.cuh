@@ -20,8 +20,11 @@ namespace vitdet {
 enum Act : int { ACT_NONE = 0, ACT_MISH = 1, ACT_GELU = 2 };
 
 // Mish(x) = x * tanh(softplus(x))  (tfa.activations.mish, reference det.py:129).
-// With n = e^x:  tanh(log(1+n)) = ((1+n)^2 - 1) / ((1+n)^2 + 1) = (n^2 + 2n) / (n^2 + 2n + 2),
-// which needs one ex2 and one rcp on the SFU instead of ex2 + lg2 + tanh.
+// With n = e^x:  tanh(log(1+n)) = ((1+n)^2 - 1) / ((1+n)^2 + 1) = 1 - 2 / (n^2 + 2n + 2), so
+//   mish(x) = x - 2x / (n^2 + 2n + 2):  one ex2 and one rcp on the SFU.
+// The fast form needs no clamp: n -> inf gives rcp(inf) = 0 and mish = x; n -> 0 gives x - x = 0.
+// It is 7 instructions (FMUL, MUFU.EX2, FADD, FFMA, MUFU.RCP, FMUL, FFMA); the epilogues of the wide
+// layers are issue/SFU-bound, so the count matters (profiles/r01b_ncu_mlp1.md: 24.5 -> 9 per element).
 template <bool PRECISE>
 __device__ __forceinline__ float mish(float x) {
     if (PRECISE) {
@@ -29,9 +32,11 @@ __device__ __forceinline__ float mish(float x) {
         float a = n * (n + 2.f);
         return x * (a / (a + 2.f));
     } else {
-        float n = __expf(fminf(x, 20.f));
-        float a = n * (n + 2.f);
-        return x * __fdividef(a, a + 2.f);
+        float n, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(x * 1.4426950408889634f));
+        const float q = fmaf(n, n + 2.f, 2.f);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+        return fmaf(x * -2.f, r, x);
     }
 }
 
@@ -159,6 +164,16 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const CUtens
         ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+
+// TMA store of a 2-D box from shared memory (bulk async-group completion).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Waits until the bulk groups of this thread have finished READING their shared-memory source.
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM -> register loads

@@ -277,6 +277,8 @@ struct vitdet_handle {
     long long launches = 0;             // kernels launched by forward_impl since the last reset
 
     // pinned staging + device buffers for predict_host
+    cudaStream_t copy_stream = nullptr;          // H2D copies of predict_host run here, overlapped with compute
+    std::vector<cudaEvent_t> copy_events;        // one per staged sub-chunk of images
     void* pin_in = nullptr; size_t pin_in_bytes = 0;
     void* pin_out = nullptr; size_t pin_out_bytes = 0;
     DevBuf dev_in, dev_out;
@@ -286,6 +288,8 @@ struct vitdet_handle {
         for (auto e : prof_pool) cudaEventDestroy(e);
         if (pin_in) cudaFreeHost(pin_in);
         if (pin_out) cudaFreeHost(pin_out);
+        for (auto e : copy_events) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -644,8 +648,18 @@ static int launch_simt(const DenseCall& c, cudaStream_t st) {
     return 0;
 }
 
+// Optional staging information of predict_host: images arrive in sub-chunks of `ready_gran` images,
+// sub-chunk i being complete when ready[i] fires; first_chunk > 0 makes the first encoder chunk small
+// so that compute starts after one sub-chunk and the rest of the copy hides behind it.
+struct ForwardOpts {
+    int first_chunk = 0;
+    const cudaEvent_t* ready = nullptr;
+    int ready_gran = 0;
+};
+
 static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, float* logits,
-                        const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st) {
+                        const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st,
+                        const ForwardOpts& opts = ForwardOpts()) {
     if (!h || !images || B <= 0) return fail(VITDET_E_INVALID, "forward: bad arguments");
     if (mode != VITDET_MODE_BF16 && mode != VITDET_MODE_FP32) return fail(VITDET_E_INVALID, "forward: unknown mode %d", mode);
     for (const WeightSlot& s : h->slots)
@@ -659,8 +673,10 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
     const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
     const int out_f32_act = bf ? 0 : 1;
 
-    for (int c0 = 0; c0 < B; c0 += h->chunk) {
-        const int bc = (B - c0) < h->chunk ? (B - c0) : h->chunk;
+    for (int c0 = 0, bc = 0; c0 < B; c0 += bc) {
+        bc = (B - c0) < h->chunk ? (B - c0) : h->chunk;
+        if (c0 == 0 && opts.first_chunk > 0 && opts.first_chunk < bc) bc = opts.first_chunk;
+        if (opts.ready) CU_TRY(cudaStreamWaitEvent(st, opts.ready[(c0 + bc + opts.ready_gran - 1) / opts.ready_gran - 1], 0));
         const int Mc = bc * T;
         float* x = h->x.as<float>() + static_cast<size_t>(c0) * T * m.D4;
         vitdet_handle::EncPlans* ep = nullptr;
@@ -1003,14 +1019,45 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     }
     RC_TRY(h->dev_in.ensure(in_bytes));
     RC_TRY(h->dev_out.ensure(out_bytes));
-    // If the caller's buffer is already page-locked, copy straight from it; otherwise stage through
-    // the handle's pinned buffer (a pageable cudaMemcpyAsync would do the same staging, serially).
+    // Images are copied in sub-chunks of kGran images on a dedicated copy stream, one event per
+    // sub-chunk; the encoder starts on a first chunk of kGran images and every later chunk waits only
+    // for its own images, so all but the first sub-chunk's copy overlaps compute.  If the caller's
+    // buffer is already page-locked the copy reads it directly; otherwise each sub-chunk is staged
+    // through the handle's pinned buffer first (what a pageable cudaMemcpyAsync would do, serially).
+    constexpr int kGran = 16;
+    const int n_sub = (B + kGran - 1) / kGran;
+    if (!h->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    while (static_cast<int>(h->copy_events.size()) < n_sub) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_events.push_back(e);
+    }
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const void* src = images_host;
-    if (!pinned) { memcpy(h->pin_in, images_host, in_bytes); src = h->pin_in; }
-    CU_TRY(cudaMemcpyAsync(h->dev_in.p, src, in_bytes, cudaMemcpyHostToDevice, st));
+    const size_t img_bytes = in_bytes / static_cast<size_t>(B);
+    {
+        // the copy stream must not overwrite dev_in while earlier work on `st` may still read it
+        cudaEvent_t e0 = h->copy_events[0];
+        CU_TRY(cudaEventRecord(e0, st));
+        CU_TRY(cudaStreamWaitEvent(h->copy_stream, e0, 0));
+    }
+    for (int i = 0; i < n_sub; ++i) {
+        const size_t off = static_cast<size_t>(i) * kGran * img_bytes;
+        const int cnt = (B - i * kGran) < kGran ? (B - i * kGran) : kGran;
+        const size_t bytes = static_cast<size_t>(cnt) * img_bytes;
+        const char* src = reinterpret_cast<const char*>(images_host) + off;
+        if (!pinned) {
+            memcpy(static_cast<char*>(h->pin_in) + off, src, bytes);
+            src = static_cast<const char*>(h->pin_in) + off;
+        }
+        CU_TRY(cudaMemcpyAsync(h->dev_in.as<char>() + off, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(cudaEventRecord(h->copy_events[i], h->copy_stream));
+    }
+    ForwardOpts opts;
+    opts.first_chunk = B > kGran ? kGran : 0;
+    opts.ready = h->copy_events.data();
+    opts.ready_gran = kGran;
     char* dbase = h->dev_out.as<char>();
     vitdet_detections d;
     d.decoded = reinterpret_cast<float*>(dbase + o_dec);
@@ -1018,7 +1065,7 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     d.class_conf = reinterpret_cast<float*>(dbase + o_cc);
     d.corners = reinterpret_cast<int32_t*>(dbase + o_cor);
     d.keep = reinterpret_cast<uint8_t*>(dbase + o_keep);
-    RC_TRY(forward_impl(h, h->dev_in.as<float>(), B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st));
+    RC_TRY(forward_impl(h, h->dev_in.as<float>(), B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st, opts));
     CU_TRY(cudaMemcpyAsync(h->pin_out, dbase, out_bytes, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     const char* pb = static_cast<const char*>(h->pin_out);

@@ -7,13 +7,16 @@
 // (bias add, MishActivation det.py:119-129 / tfa GELU det.py:402, keras.layers.add det.py:305,
 // 371, 408-412), which run here as the epilogue of the same kernel.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 576 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of A (128 x 64 bf16) and W (BN x 64
 //               bf16) into a ring of 128B-swizzled shared-memory stages, completion on mbarriers.
 //   warp 1      allocates 512 TMEM columns; one elected lane issues tcgen05.mma (M=128, N=BN, K=16,
 //               bf16 x bf16 -> f32 in TMEM) and tcgen05.commit to free stages / publish accumulators.
-//   warps 2..5  epilogue: tcgen05.ld the f32 accumulator (thread = one row of the tile), bias /
-//               position scalar / activation / residual, 16-byte global stores.
+//   warps 2..17 epilogue: tcgen05.ld the f32 accumulator (thread = one row of the tile, the four warps
+//               of a TMEM lane quadrant split the 32-column chunks), bias / position scalar /
+//               activation / residual, 16-byte global stores.  Sixteen warps because the Mish epilogue
+//               of the wide layers is issue-bound: with four it capped the 28 -> 3584 layer at 5x its
+//               HBM time (profiles/r01a_ncu_gemm.md).
 // Two TMEM accumulator stages (2 x 256 columns) let the MMA of tile i+1 overlap the epilogue of
 // tile i.  BN and the ring depth are run-time values (N lives in the instruction descriptor), so one
 // binary serves every layer width of the model.
@@ -30,11 +33,16 @@ constexpr int kUK = 16;               // UMMA K for 16-bit inputs
 constexpr int kMaxBN = 256;
 constexpr int kMaxStages = 8;
 constexpr int kStageBytesA = kBM * kBK * 2;   // 16 KiB
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant; the quadrant's warps split the 32-column chunks
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kTmemCols = 512;
-constexpr int kRingBytes = 200 * 1024;            // budget of the A/B stage ring
-constexpr int kMaxDynSmem = kRingBytes + 1024;    // + alignment slack; static smem (~2.2 KB) must also fit in 227 KB
+constexpr int kRingBytes = 192 * 1024;            // budget of the A/B stage ring (4 stages at BN = 256)
+constexpr int kStoreTileBytes = 32 * 32 * 2;      // one epilogue warp's 32 x 32 bf16 sub-tile, 64B-swizzled
+constexpr int kStoreBytes = kEpiWarps * kStoreTileBytes;
+// Dynamic smem = ring + store staging = 224 KB; the static part (barriers, bias, ~2.2 KB) is padded to
+// 3 KB by the 1024-byte alignment of the dynamic part, which makes exactly 227 KB.
+constexpr int kMaxDynSmem = kRingBytes + kStoreBytes;
 
 struct TcGemmArgs {
     int M, N, K;
@@ -56,8 +64,8 @@ struct TcGemmArgs {
 template <int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcGemmArgs p) {
-    extern __shared__ uint8_t smem_raw[];
+               const __grid_constant__ CUtensorMap tmC, const TcGemmArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[2][kMaxBN];
@@ -65,7 +73,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0u) __trap();          // 128B-swizzled stages need 1024-byte alignment
+    const uint32_t s_store0 = smem_base + kRingBytes; // epilogue store staging, one 2 KB tile per warp
     const uint32_t stage_bytes_b = static_cast<uint32_t>(p.block_n) * (kBK * 2);
     const uint32_t sA0 = smem_base;
     const uint32_t sB0 = smem_base + static_cast<uint32_t>(p.num_stages) * kStageBytesA;
@@ -82,13 +92,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, kEpiThreads);
+            mbar_init(bar_tempty + 8 * a, kEpiWarps);
         }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (!OUT_F32) tma_prefetch_desc(&tmC);
     }
     if (warp == 1) {
         tmem_alloc(smem_u32(&tmem_base_s), kTmemCols);
@@ -149,8 +160,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ------------------------------ epilogue ----------------------------------
+        // Warp w may only read TMEM lanes [32*(w%4), +32).  The four warps of a quadrant take the
+        // 32-column chunks round-robin (sub = 0..3), so a 256-wide tile is two chunks per warp.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int et = threadIdx.x - 64;              // 0..127 within the epilogue group
+        const int sub = (warp - 2) >> 2;              // which chunks of the tile (c0 = 32*sub, +128, ...)
+        const int et = threadIdx.x - 64;              // 0..kEpiThreads-1 within the epilogue group
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -159,11 +173,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n0 = (tile % p.n_tiles) * p.block_n;
 
             // Stage this tile's bias slice in shared memory (double-buffered by tile parity; the
-            // single named barrier per tile also orders reuse of the other buffer, see DESIGN.md).
+            // single named barrier per tile also orders reuse of the other buffer).
             float* bs = bias_s[it & 1];
-            for (int c = et; c < p.block_n; c += kEpiThreads) {
-                const int n = n0 + c;
-                bs[c] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+            if (et < p.block_n) {
+                const int n = n0 + et;
+                bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 
@@ -177,66 +191,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * kMaxBN);
 
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            for (int c0 = sub * 32; c0 < p.block_n; c0 += 128) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c0, v);
                 tmem_ld_wait();
-                if (row_ok) {
-                    if (OUT_F32) {
-                        float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc;
-                        const float* rrow = p.resid ? p.resid + static_cast<size_t>(row) * p.ldr : nullptr;
+                const bool full = n0 + c0 + 32 <= p.N;      // block_n is a multiple of 32: chunks are never partial in the tile
+                if (OUT_F32) {
+                    if (!row_ok) continue;
+                    float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc;
+                    const float* rrow = p.resid ? p.resid + static_cast<size_t>(row) * p.ldr : nullptr;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int c = c0 + 4 * g;
+                        const int n = n0 + c;
+                        if (full || n < p.n_store) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c);
+                            float x[4] = {__uint_as_float(v[4 * g + 0]) + b4.x, __uint_as_float(v[4 * g + 1]) + b4.y,
+                                          __uint_as_float(v[4 * g + 2]) + b4.z, __uint_as_float(v[4 * g + 3]) + b4.w};
+                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
+                            const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float y = apply_act<ACT, false>(x[j] + pos_v) + r[j];
+                                x[j] = (full || n + j < p.N) ? y : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
+                        }
+                    }
+                } else {
+                    // bf16 output: this warp's 32 x 32 sub-tile goes to its 64B-swizzled staging tile
+                    // (row = lane, 64 B per row; 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3),
+                    // which is both what CU_TENSOR_MAP_SWIZZLE_64B expects and bank-conflict free), then
+                    // one TMA store writes it with full 64-byte row segments.  Rows >= M and columns past
+                    // the tensor width are clipped by the TMA unit.
+                    const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp - 2) * kStoreTileBytes;
+                    uint32_t o[16];
+                    if (full) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            const int c = c0 + 4 * g;
-                            const int n = n0 + c;
-                            if (c < p.block_n && n < p.n_store) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bs + c);
-                                float x[4] = {__uint_as_float(v[4 * g + 0]) + b4.x,
-                                              __uint_as_float(v[4 * g + 1]) + b4.y,
-                                              __uint_as_float(v[4 * g + 2]) + b4.z,
-                                              __uint_as_float(v[4 * g + 3]) + b4.w};
-                                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
-                                const float r[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float y = apply_act<ACT, false>(x[j] + pos_v) + r[j];
-                                    x[j] = (n + j < p.N) ? y : 0.f;
-                                }
-                                *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
-                            }
+                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 0]) + b4.x);
+                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 1]) + b4.y);
+                            const float y2 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 2]) + b4.z);
+                            const float y3 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 3]) + b4.w);
+                            o[2 * g] = pack_bf16x2(y0, y1);
+                            o[2 * g + 1] = pack_bf16x2(y2, y3);
                         }
-                    } else {
-                        __nv_bfloat16* orow =
-                            reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldc;
+                    } else {      // last N tile: columns >= N are written as zero
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int c = c0 + 8 * g;
-                            const int n = n0 + c;
-                            if (c < p.block_n && n < p.n_store) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(bs + c);
-                                const float4 b1 = *reinterpret_cast<const float4*>(bs + c + 4);
-                                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                                float x[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float y = apply_act<ACT, false>(__uint_as_float(v[8 * g + j]) + b[j] + pos_v);
-                                    x[j] = (n + j < p.N) ? y : 0.f;
-                                }
-                                uint4 o;
-                                o.x = pack_bf16x2(x[0], x[1]);
-                                o.y = pack_bf16x2(x[2], x[3]);
-                                o.z = pack_bf16x2(x[4], x[5]);
-                                o.w = pack_bf16x2(x[6], x[7]);
-                                *reinterpret_cast<uint4*>(orow + n) = o;
-                            }
+                        for (int g = 0; g < 16; ++g) {
+                            const int n = n0 + c0 + 2 * g;
+                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 0]) + bs[c0 + 2 * g]);
+                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 1]) + bs[c0 + 2 * g + 1]);
+                            o[g] = pack_bf16x2(n < p.N ? y0 : 0.f, n + 1 < p.N ? y1 : 0.f);
                         }
+                    }
+                    // only now wait for the previous TMA store of this warp to have left the staging
+                    // tile: its read latency is hidden behind the arithmetic above
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t dst = s_tile + static_cast<uint32_t>(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * g]), "r"(o[4 * g + 1]),
+                                     "r"(o[4 * g + 2]), "r"(o[4 * g + 3]) : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, s_tile, n0 + c0, m0 + quad * 32);
+                        tma_store_commit();
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (!OUT_F32 && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -277,18 +310,19 @@ cudaError_t launch_variant(const TcGemmPlan& plan, const TcGemmArgs& a, cudaStre
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, a);
+    kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int choose_block_n(int N) {
-    if (N <= kMaxBN) return (N + 15) / 16 * 16;
-    // Largest multiple of 16 whose padded width wastes <= 3 %; otherwise the least wasteful >= 64.
+    // Multiples of 32: the epilogue works on 32-column chunks (one tcgen05.ld, one TMA store box).
+    if (N <= kMaxBN) return (N + 31) / 32 * 32;
+    // Largest multiple of 32 whose padded width wastes <= 3 %; otherwise the least wasteful >= 64.
     int best = kMaxBN;
     double best_waste = 1e9;
-    for (int bn = kMaxBN; bn >= 64; bn -= 16) {
+    for (int bn = kMaxBN; bn >= 64; bn -= 32) {
         const int tiles = (N + bn - 1) / bn;
         const double waste = static_cast<double>(tiles) * bn / N - 1.0;
         if (waste <= 0.03) return bn;
@@ -299,17 +333,25 @@ int choose_block_n(int N) {
 
 // 2-D bf16 tensor map, row-major [rows, cols] with `ld` elements between rows, box = 64 x box_rows,
 // 128B swizzle, out-of-bounds elements read as zero (this is what pads K, M and N tails).
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_tmap_bf16_2d_ex(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows,
+                         int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    return make_tmap_bf16_2d_ex(map, base, rows, cols, ld, kBK, box_rows, 128);
 }
 
 int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
@@ -321,8 +363,9 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     const int vec = d.out_f32 ? 4 : 8;
     if ((d.ldc % vec) || d.ldc < (d.N + vec - 1) / vec * vec) return -5;
     if (d.resid && (!d.out_f32 || (d.ldr % 4) || d.ldr < (d.N + 3) / 4 * 4)) return -6;
+    if (d.pos && !d.out_f32) return -8;      // the position scalar is only fused into f32-output layers
     int bn = d.block_n > 0 ? d.block_n : choose_block_n(d.N);
-    if (bn % 16 || bn < 16 || bn > kMaxBN) return -7;
+    if (bn % 32 || bn < 32 || bn > kMaxBN) return -7;
 
     plan->desc = d;
     plan->block_n = bn;
@@ -330,7 +373,7 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     int stages = kRingBytes / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     plan->num_stages = stages;
-    plan->smem_bytes = static_cast<size_t>(stages) * stage + 1024;
+    plan->smem_bytes = kMaxDynSmem;    // ring (up to 192 KB) + store staging, fixed layout
     const int m_tiles = (d.M + kBM - 1) / kBM;
     const int n_tiles = (d.N + bn - 1) / bn;
     plan->n_tiles = n_tiles;
@@ -339,6 +382,13 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, d.K, d.lda, kBM);
     if (r) return r;
     r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, d.K, d.ldw, bn);
+    if (r) return r;
+    if (!d.out_f32) {
+        // store map: columns [N, round_up(N, 8)) are part of the tensor and receive zeros
+        r = make_tmap_bf16_2d_ex(&plan->tmC, d.out, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
+    } else {
+        plan->tmC = plan->tmA;     // unused by the f32-output instantiations
+    }
     return r;
 }
 

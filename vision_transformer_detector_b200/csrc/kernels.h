@@ -35,6 +35,7 @@ struct GemmDesc {
 
 struct TcGemmPlan {
     CUtensorMap tmA, tmB;
+    CUtensorMap tmC;           // bf16 outputs only: 32 x 32 boxes, 64B swizzle (TMA store from the epilogue)
     GemmDesc desc;
     int block_n = 0;
     int num_stages = 0;
@@ -46,6 +47,7 @@ struct TcGemmPlan {
 
 int choose_block_n(int N);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
+int make_tmap_bf16_2d_ex(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows, int swizzle_bytes);
 int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms);
 cudaError_t tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
 
