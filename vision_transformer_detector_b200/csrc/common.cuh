@@ -209,6 +209,20 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: A (bf16, 128 rows = lanes, two K elements per 32-bit column) read from
+// tensor memory, B through a shared-memory descriptor.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // All previously issued tcgen05.mma of this thread arrive (once) on `bar` when they complete.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -231,6 +245,29 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// Register -> TMEM stores, same lane/column addressing as the loads.
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -250,12 +287,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major operand tile (the N/M index is contiguous): rows are K steps of 128 B (64 bf16 along MN),
+// 8 rows form a 1024 B swizzle atom; what a TMA box of 64 bf16 x R rows produces for a matrix stored
+// [K][MN].  SBO = 1024 B between 8-row K groups; LBO (stride between 64-element MN chunks) unused for
+// MN <= 64.  Used for V in the attention PV product.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr) {
+    return umma_desc_sw128_kmajor(smem_addr);     // same fields; the major-ness lives in the instruction descriptor
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), f32 accumulator, M x N tile:
 //   [4,6) c_format = 1 (f32)   [7,10) a_format = 1 (bf16)   [10,13) b_format = 1 (bf16)
 //   bit 15 / 16 a_major / b_major = 0 (K-major)   [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
+}
+// Same with B MN-major (bit 16).
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_f32_bmn(int m, int n) {
+    return umma_idesc_bf16_f32(m, n) | (1u << 16);
 }
 
 }  // namespace vitdet

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -60,6 +61,16 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// VITDET_ATTN=legacy selects the mma.sync attention kernel, for A/B measurements only.
+static bool use_legacy_attention() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITDET_ATTN"); v = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
+    return v == 1;
+}
+static cudaError_t attn_launch(const AttnPlan& plan, cudaStream_t st) {
+    return use_legacy_attention() ? attn_bf16_launch(plan, st) : attn_tc_launch(plan, st);
+}
 
 constexpr int kHeadPitch = 64;   // elements per head slot in qkv / ctx (one 128-byte swizzle row of bf16)
 
@@ -702,7 +713,7 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
             CU_TRY(layernorm_launch(x, m.D4, b.ln1_g.as<float>(), b.ln1_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
             if (bf) {
                 { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_tc(ep->qkv[i], h->qkv.p, nullptr, st)); }
-                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_bf16_launch(ep->attn[i], st)); }
+                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_launch(ep->attn[i], st)); }
                 { ProfScope ps(h, PC_OUT, st); RC_TRY(launch_tc(ep->out[i], x, x, st)); }
             } else {
                 DenseCall qc{h->y.p, ldy, &b.qkv, nullptr, 1, nullptr, 0, h->qkv.p, m.w_qkv, 1, ACT_NONE, Mc};
@@ -1166,7 +1177,7 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
         AttnPlan plan;
         int rc = attn_bf16_make_plan(&plan, ad);
         if (rc) return fail(VITDET_E_INVALID, "op_attention: attn_bf16_make_plan failed: %d", rc);
-        CU_TRY(attn_bf16_launch(plan, st));
+        CU_TRY(attn_launch(plan, st));
         unpack_ctx_kernel<__nv_bfloat16><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<__nv_bfloat16>(), rows, H, d, hp, out);
     } else {
         pack_qkv_kernel<float><<<blocks_for(rows * 3 * H * hp), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<float>());
