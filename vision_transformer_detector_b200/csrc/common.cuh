@@ -128,6 +128,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Wait used where latency does not matter (a producer running stages ahead): back off with nanosleep
+// so that the polling lane does not steal issue slots from the compute warps of its sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(200);
+        if ((++polls & 0x3ffu) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — tiled 2-D loads into 128B-swizzled shared memory
 // ---------------------------------------------------------------------------------------------
