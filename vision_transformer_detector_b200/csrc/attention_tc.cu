@@ -4,21 +4,23 @@
 //
 // One CTA = 128 queries of one (image, head); two CTAs are resident per SM so that the softmax of one
 // overlaps the softmax latencies of the other.  192 threads:
-//   warp 0      TMA producer: Q once, then 64-key K and V tiles (cp.async.bulk.tensor, 128B swizzle)
-//               through a 4-stage mbarrier ring.
+//   warp 0      TMA producer: Q once, then 128-key K and V tiles (cp.async.bulk.tensor, 128B swizzle)
+//               through a 3-stage mbarrier ring.
 //   warp 1      allocates 256 TMEM columns; one lane issues
-//                 S[j&1] = Q K(j)^T   tcgen05.mma  M128 x N64 x K(16*ceil(d/16)), A and B K-major from smem
-//                 O += P V(j)         tcgen05.mma  M128 x N64 x K64, A = P from TENSOR MEMORY, B = V MN-major
-//               S is double-buffered, so QK^T runs up to two tiles ahead of the softmax.
-//   warps 2..5  softmax: thread = query row (TMEM lane).  One tcgen05.ld pass brings the 64 scores of
+//                 S = Q K(j)^T        tcgen05.mma  M128 x N128 x K(16*ceil(d/16)), A and B K-major from smem
+//                 O += P V(j)         tcgen05.mma  M128 x N64 x K128, A = P from TENSOR MEMORY, B = V MN-major
+//               QK^T(j+1) is issued as soon as the softmax warps have S(j) in registers.
+//   warps 2..5  softmax: thread = query row (TMEM lane).  One tcgen05.ld pass brings the 128 scores of
 //               the row into registers (S is released to the MMA warp immediately), row maximum without
 //               shuffles, p = ex2(s*c - m), row sum, P written back to TMEM as packed bf16 (tcgen05.st) —
 //               never through shared memory.  The running maximum is only advanced (and O rescaled in
 //               TMEM) when it grew by more than 2^8, so most tiles skip the correction.
-// TMEM columns: S0 [0,64) f32 | S1 [64,128) f32 | P [128,160) bf16x2 | O [192,256) f32.
+// TMEM columns: S [0,128) f32 | P [128,192) bf16x2 | O [192,256) f32.
 //
-// The binding unit is the SFU, not the tensor pipe: per 128 x 64 score tile the CTA needs 8192 ex2 at
-// 16/clk/SM = 512 clk, against ~230 clk of MMA at head_dim 40.
+// The binding unit is the SFU, not the tensor pipe: per 128 x 128 score tile the CTA needs 16 384 ex2 at
+// 16/clk/SM = 1024 clk, against ~450 clk of MMA at head_dim 40.  Tiles of 128 keys (not 64)
+// because the per-tile fixed costs (barrier round trips, TMEM load/store latency) are what keeps the
+// SFU idle (profiles/r01c_*).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -27,14 +29,15 @@ namespace vitdet {
 namespace {
 
 constexpr int kQ = 128;            // queries per CTA (UMMA M)
-constexpr int kKV = 64;            // keys per tile (UMMA N of QK^T, K of PV)
+constexpr int kKV = 128;           // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kHP = 64;            // head pitch in elements (one 128-byte swizzle row of bf16)
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kThreads = 192;
 constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
-constexpr int kTileBytes = kKV * kHP * 2;     // 8 KiB: one K tile or one V tile = one TMA box
+constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one K tile or one V tile = two TMA boxes of 64 rows
+constexpr int kBoxBytes = 64 * kHP * 2;
 constexpr int kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;   // S [0,128) f32 | P [128,192) bf16x2 | O [192,256) f32
 constexpr float kRescaleThreshold = 8.f;      // log2 units: P stays <= 2^8 between rescales
 
 struct AttnTcArgs {
@@ -54,7 +57,7 @@ __device__ __forceinline__ float ex2f(float x) {
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 8];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 5];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5;
@@ -72,10 +75,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     const uint32_t bar_full = smem_u32(&bars[0]);
     const uint32_t bar_empty = smem_u32(&bars[kStages]);
     const uint32_t bar_q = smem_u32(&bars[2 * kStages]);
-    const uint32_t bar_s_full = smem_u32(&bars[2 * kStages + 1]);   // [2] QK^T(j) complete in S[j&1]   (MMA commit)
-    const uint32_t bar_s_free = smem_u32(&bars[2 * kStages + 3]);   // [2] S[j&1] is in registers       (4 warps)
-    const uint32_t bar_p_full = smem_u32(&bars[2 * kStages + 5]);   // P(j) (and rescaled O) in TMEM    (4 warps)
-    const uint32_t bar_pv_done = smem_u32(&bars[2 * kStages + 6]);  // PV(j) complete                   (MMA commit)
+    const uint32_t bar_s_full = smem_u32(&bars[2 * kStages + 1]);   // QK^T(j) complete                 (MMA commit)
+    const uint32_t bar_s_free = smem_u32(&bars[2 * kStages + 2]);   // S(j) is in registers             (4 warps)
+    const uint32_t bar_p_full = smem_u32(&bars[2 * kStages + 3]);   // P(j) (and rescaled O) in TMEM    (4 warps)
+    const uint32_t bar_pv_done = smem_u32(&bars[2 * kStages + 4]);  // PV(j) complete                   (MMA commit)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -83,10 +86,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_q, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_s_full + 8 * i, 1);
-            mbar_init(bar_s_free + 8 * i, 4);
-        }
+        mbar_init(bar_s_full, 1);
+        mbar_init(bar_s_free, 4);
         mbar_init(bar_p_full, 4);
         mbar_init(bar_pv_done, 1);
         fence_mbar_init();
@@ -106,7 +107,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             tma_prefetch_desc(&tmQKV);
             mbar_arrive_expect_tx(bar_q, kQBytes);
             tma_load_2d(sQ, &tmQKV, bar_q, h * kHP, row_base + q0);
-            tma_load_2d(sQ + kQBytes / 2, &tmQKV, bar_q, h * kHP, row_base + q0 + 64);
+            tma_load_2d(sQ + kBoxBytes, &tmQKV, bar_q, h * kHP, row_base + q0 + 64);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < nkv; ++j) {
@@ -115,7 +116,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                 const uint32_t dK = sKV + stage * 2 * kTileBytes;
                 const int r = row_base + j * kKV;
                 tma_load_2d(dK, &tmQKV, bar_full + 8 * stage, (p.H + h) * kHP, r);
+                tma_load_2d(dK + kBoxBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * kHP, r + 64);
                 tma_load_2d(dK + kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * kHP, r);
+                tma_load_2d(dK + kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * kHP, r + 64);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -131,15 +134,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             uint32_t phase = 0;
             for (int j = 0; j <= nkv; ++j) {
                 if (j < nkv) {
-                    // S[j&1] = Q K(j)^T; the buffer was last read for tile j-2
-                    const int sb = j & 1;
+                    // S = Q K(j)^T; the softmax warps moved S(j-1) into registers before signalling s_free
                     mbar_wait(bar_full + 8 * stage, phase);
-                    if (j >= 2) mbar_wait(bar_s_free + 8 * sb, ((j - 2) >> 1) & 1);
+                    if (j >= 1) mbar_wait(bar_s_free, (j - 1) & 1);
                     tc_fence_after();
                     const uint64_t dk = umma_desc_sw128_kmajor(sKV + stage * 2 * kTileBytes);
-                    const uint32_t tS = tmem_base + kColS + 64u * sb;
+                    const uint32_t tS = tmem_base + kColS;
                     for (int k = 0; k < p.k16; ++k) umma_bf16_ss(tS, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0);
-                    umma_commit(bar_s_full + 8 * sb);
+                    umma_commit(bar_s_full);
                 }
                 if (j > 0) {
                     // O += P(j-1) V(j-1)
@@ -164,34 +166,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         float m_used = -INFINITY;      // running maximum in the scaled log2 domain
         float l = 0.f;                 // running sum of p
         for (int j = 0; j < nkv; ++j) {
-            const int sb = j & 1;
             const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
-            const uint32_t tS = tmem_base + lane_off + kColS + 64u * sb;
-            mbar_wait(bar_s_full + 8 * sb, (j >> 1) & 1);
+            const uint32_t tS = tmem_base + lane_off + kColS;
+            mbar_wait(bar_s_full, j & 1);
             tc_fence_after();
 
-            // the whole row slice into registers, then S[sb] belongs to the MMA warp again
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(tS, v0);
-            tmem_ld_32x32(tS + 32u, v1);
+            // the whole row slice into registers (four loads in flight, one wait), then S belongs to the
+            // MMA warp again and QK^T(j+1) overlaps this tile's softmax
+            uint32_t v[4][32];
+            tmem_ld_32x32(tS, v[0]);
+            tmem_ld_32x32(tS + 32u, v[1]);
+            tmem_ld_32x32(tS + 64u, v[2]);
+            tmem_ld_32x32(tS + 96u, v[3]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_s_free + 8 * sb);
+            if (lane == 0) mbar_arrive(bar_s_free);
 
-            float s[64];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(v0[i]); s[32 + i] = __uint_as_float(v1[i]); }
             if (valid < kKV) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) s[i] = (i < valid) ? s[i] : -INFINITY;     // keys past the end of the image
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (32 * c + i >= valid) v[c][i] = 0xff800000u;     // -inf: keys past the end of the image
             }
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-                mx[0] = fmaxf(mx[0], s[i]); mx[1] = fmaxf(mx[1], s[i + 1]);
-                mx[2] = fmaxf(mx[2], s[i + 2]); mx[3] = fmaxf(mx[3], s[i + 3]);
-            }
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
+                    mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
+                }
             const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2);
             const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile
             float alpha = 1.f;
@@ -202,17 +208,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             }
             const float neg_m = -m_used;
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t pk[32];
+            // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-                const float e0 = ex2f(fmaf(s[i], p.scale_log2, neg_m));          // ex2(-inf) = 0 for masked keys
-                const float e1 = ex2f(fmaf(s[i + 1], p.scale_log2, neg_m));
-                const float e2 = ex2f(fmaf(s[i + 2], p.scale_log2, neg_m));
-                const float e3 = ex2f(fmaf(s[i + 3], p.scale_log2, neg_m));
-                sum[0] += e0; sum[1] += e1; sum[2] += e2; sum[3] += e3;
-                pk[i / 2] = pack_bf16x2(e0, e1);
-                pk[i / 2 + 1] = pack_bf16x2(e2, e3);
-            }
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float e0 = ex2f(fmaf(__uint_as_float(v[c][i]), p.scale_log2, neg_m));      // ex2(-inf) = 0
+                    const float e1 = ex2f(fmaf(__uint_as_float(v[c][i + 1]), p.scale_log2, neg_m));
+                    const float e2 = ex2f(fmaf(__uint_as_float(v[c][i + 2]), p.scale_log2, neg_m));
+                    const float e3 = ex2f(fmaf(__uint_as_float(v[c][i + 3]), p.scale_log2, neg_m));
+                    sum[0] += e0; sum[1] += e1; sum[2] += e2; sum[3] += e3;
+                    v[c][i / 2] = pack_bf16x2(e0, e1);
+                    v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
+                }
             l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
 
             // P and O must no longer be in use by PV(j-1)
@@ -231,7 +239,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                     }
                 }
             }
-            tmem_st_32x32_x32(tP, pk);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = v[c][i];
+                tmem_st_32x32_x16(tP + 16u * c, pk);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
