@@ -1,13 +1,17 @@
 # One GPU visit: full GPU test-suite, N=1 bench with per-kernel breakdown, ncu launch list, ncu --set full of the top kernels.
 mkdir -p gpurun_out
+rm -f gpurun_out/*.ncu-rep
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 --breakdown > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+timeout 900 python bench.py --steps 10 --warmup 3 --breakdown > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cut -c1-400 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 timeout 600 $BENCH > gpurun_out/plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 360 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
+# gemm_tc_kernel launches in one forward: proj(0) | per block: qkv, out, mlp1..8 -> indices 3 = mlp_1, 4 = mlp_2, 5 = mlp_3 of block 1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 3 -f -o gpurun_out/prof_gemm $BENCH > gpurun_out/ncu_gemm.log 2>&1
 echo "ncu gemm rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_bf16_kernel -s 1 -c 1 -f -o gpurun_out/prof_attn $BENCH > gpurun_out/ncu_attn.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_attn_tc $BENCH > gpurun_out/ncu_attn.log 2>&1
 echo "ncu attn rc=$?"
-ls -la gpurun_out/
+timeout 900 ncu --set full --clock-control none -k regex:"layernorm_kernel|patchify_kernel|head_tail_kernel|head_slots_kernel" -c 4 -f -o gpurun_out/prof_rowops $BENCH > gpurun_out/ncu_rowops.log 2>&1
+echo "ncu rowops rc=$?"
+ls -la gpurun_out/ | head -30
