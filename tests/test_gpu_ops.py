@@ -28,6 +28,8 @@ DENSE_SHAPES = [
     (34, 1296, 8704),     # head, M = 2 images x 17 slots
     (34, 272, 136),
     (1, 64, 16), (127, 70, 17), (128, 16, 8), (130, 200, 300),
+    # M >= 1024 and N >= 128: the CTA-pair (cta_group::2) kernel; M tails on one or both CTAs of the last pair
+    (4096, 3584, 1792), (1024, 64, 128), (1100, 200, 300), (1300, 28, 3584), (2592, 896, 448),
 ]
 
 

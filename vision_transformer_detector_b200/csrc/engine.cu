@@ -461,9 +461,26 @@ static GemmDesc make_desc(const DenseCall& c, int mode) {
     return g;
 }
 
+// The CTA-pair kernel (gemm_tc2.cu) serves the layers with enough rows, columns and depth to fill 256 x BN
+// cluster tiles; VITDET_GEMM_PAIR=0 forces the single-CTA kernel everywhere, =all the pair kernel wherever it
+// is legal (A/B measurements and tests).
+// Measured (B = 64): 3 % faster on the MMA-bound layers (3584 -> 1792 -> 896 -> 448), slower on the K = 28
+// layers whose time is the epilogue (the pair couples both CTAs' epilogues), hence the K threshold.
+static bool use_pair_kernel(int M, int N, int K) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITDET_GEMM_PAIR"); v = (e && strcmp(e, "0") == 0) ? 0 : (e && strcmp(e, "all") == 0) ? 2 : 1; }
+    if (v == 0 || M < 1024 || N < 128) return false;
+    return v == 2 || K >= 512;
+}
+
+static int make_tc_plan(TcGemmPlan* plan, const GemmDesc& g, int num_sms) {
+    plan->pair = use_pair_kernel(g.M, g.N, g.K) ? 1 : 0;
+    return plan->pair ? tc2_gemm_make_plan(plan, g, num_sms) : tc_gemm_make_plan(plan, g, num_sms);
+}
+
 static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
     GemmDesc g = make_desc(c, VITDET_MODE_BF16);
-    int rc = tc_gemm_make_plan(plan, g, h->num_sms);
+    int rc = make_tc_plan(plan, g, h->num_sms);
     if (rc) return fail(VITDET_E_INVALID, "tc_gemm_make_plan(M=%d N=%d K=%d lda=%d ldc=%d) failed: %d", g.M, g.N, g.K, g.lda, g.ldc, rc);
     return 0;
 }
@@ -647,7 +664,7 @@ static int launch_tc(TcGemmPlan plan /*by value: out / resid are patched per lau
                      cudaStream_t st) {
     plan.desc.out = out;
     plan.desc.resid = resid;
-    cudaError_t e = tc_gemm_launch(plan, st);
+    cudaError_t e = plan.pair ? tc2_gemm_launch(plan, st) : tc_gemm_launch(plan, st);
     if (e != cudaSuccess) return fail(VITDET_E_CUDA, "tc_gemm_launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -1123,7 +1140,7 @@ int vitdet_op_dense(const float* A, const float* kernel, const float* bias, cons
         DenseCall c{a_buf.p, K8, &w, nullptr, 1, rp, N4, o_buf.p, N4, 1, act, M};
         TcGemmPlan plan;
         GemmDesc g = make_desc(c, VITDET_MODE_BF16);
-        rc = tc_gemm_make_plan(&plan, g, sms);
+        rc = make_tc_plan(&plan, g, sms);
         if (rc) return fail(VITDET_E_INVALID, "op_dense: tc_gemm_make_plan failed: %d", rc);
         RC_TRY(launch_tc(plan, o_buf.p, rp, st));
     } else {

@@ -1,0 +1,376 @@
+// Dense layer on the 5th-gen tensor cores with CTA PAIRS (cta_group::2):  out = epilogue( A[M,K] * W[N,K]^T ).
+//
+// Same contract and epilogue as gemm_tc.cu; used for the large layers (the 3584 -> 1792 MLP layer is 37 %
+// of the forward).  Two CTAs on the two SMs of a TPC form a cluster and compute one 256 x BN tile:
+// each CTA stages ITS 128 rows of A and HALF of the BN rows of W per k-block, the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256), and each CTA's TMEM receives the accumulator of its own 128 rows.
+// Per SM and per MMA the tensor core then reads 4 KB (A) + 4 KB (half of B) of shared memory instead of
+// 4 + 8 KB, and TMA fills 32 KB per k-block instead of 48 KB: the single-CTA kernel sat at 81 % tensor-pipe
+// activity with the shared-memory operand pipe at 75 % of its rate (profiles/r01b_ncu_gemm.md).
+//   warp 0      TMA producer (both CTAs): own A box + own half of the W box; completion is signalled on
+//               the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2).
+//   warp 1      TMEM allocation (both CTAs); in the leader one lane issues the MMAs and commits with
+//               multicast so that both CTAs' "stage empty" / "accumulator full" barriers fire.
+//   warps 2..17 epilogue of the CTA's own 128 rows, as in gemm_tc.cu; "accumulator drained" arrives on the
+//               leader's barrier from both CTAs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vitdet {
+
+namespace {
+
+constexpr int kBM = 128;              // UMMA M (cta_group::1)
+constexpr int kBK = 64;               // one 128-byte swizzle row of bf16
+constexpr int kUK = 16;               // UMMA K for 16-bit inputs
+constexpr int kMaxBN = 256;
+constexpr int kMaxStages = 8;
+constexpr int kStageBytesA = kBM * kBK * 2;   // 16 KiB
+constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant; the quadrant's warps split the 32-column chunks
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kTmemCols = 512;
+constexpr int kRingBytes = 192 * 1024;            // budget of the A/B stage ring (4 stages at BN = 256)
+constexpr int kStoreTileBytes = 32 * 32 * 2;      // one epilogue warp's 32 x 32 bf16 sub-tile, 64B-swizzled
+constexpr int kStoreBytes = kEpiWarps * kStoreTileBytes;
+// Dynamic smem = ring + store staging = 224 KB; the static part (barriers, bias, ~2.2 KB) is padded to
+// 3 KB by the 1024-byte alignment of the dynamic part, which makes exactly 227 KB.
+constexpr int kMaxDynSmem = kRingBytes + kStoreBytes;
+
+struct Tc2GemmArgs {
+    int M, N, K;
+    int block_n;
+    int num_stages;
+    int n_tiles;
+    int num_tiles;
+    int num_kb;
+    const float* bias;
+    const float* pos;
+    int pos_period;
+    const float* resid;
+    int ldr;
+    void* out;
+    int ldc;
+    int n_store;   // round_up(N, store vector): columns [N, n_store) are written as zero
+};
+
+template <int ACT, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const Tc2GemmArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[2][kMaxBN];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0u) __trap();          // 128B-swizzled stages need 1024-byte alignment
+    const uint32_t s_store0 = smem_base + kRingBytes; // epilogue store staging, one 2 KB tile per warp
+    const uint32_t stage_bytes_b = static_cast<uint32_t>(p.block_n / 2) * (kBK * 2);      // this CTA's half of the W tile
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const uint32_t sA0 = smem_base;
+    const uint32_t sB0 = smem_base + static_cast<uint32_t>(p.num_stages) * kStageBytesA;
+
+    const uint32_t bar_full = smem_u32(&bars[0]);
+    const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+    const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 2 * kEpiWarps);     // leader's copy collects both CTAs' epilogue warps
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (!OUT_F32) tma_prefetch_desc(&tmC);
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(smem_u32(&tmem_base_s), kTmemCols);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();            // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            // this CTA's loads complete on the LEADER's full barrier (same offset, CTA rank 0)
+            const uint32_t bar_full_leader = mapa_shared(bar_full, 0);
+            const uint32_t tx_bytes = 2u * (kStageBytesA + stage_bytes_b);       // both CTAs' boxes
+            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1) {
+                const int m0 = (tile / p.n_tiles) * (2 * kBM) + static_cast<int>(cta_rank) * kBM;
+                const int n0 = (tile % p.n_tiles) * p.block_n + static_cast<int>(cta_rank) * (p.block_n / 2);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+                    tma_load_2d_2sm(sA0 + stage * kStageBytesA, &tmA, bar_full_leader + 8 * stage, kb * kBK, m0);
+                    tma_load_2d_2sm(sB0 + stage * stage_bytes_b, &tmB, bar_full_leader + 8 * stage, kb * kBK, n0);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer (leader CTA only) --------------
+        if (leader && lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(2 * kBM, p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128_kmajor(sA0 + stage * kStageBytesA);
+                    const uint64_t db = umma_desc_sw128_kmajor(sB0 + stage * stage_bytes_b);
+                    int ksteps = kBK / kUK;
+                    if (kb == p.num_kb - 1) ksteps = (p.K - kb * kBK + kUK - 1) / kUK;
+                    for (int k = 0; k < ksteps; ++k) umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(bar_empty + 8 * stage, 3);          // frees the stage in both CTAs
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_2sm(bar_tfull + 8 * acc, 3);                // accumulators of both CTAs are complete
+            }
+        }
+    } else {
+        // ------------------------------ epilogue ----------------------------------
+        // Warp w may only read TMEM lanes [32*(w%4), +32).  The four warps of a quadrant take the
+        // 32-column chunks round-robin (sub = 0..3), so a 256-wide tile is two chunks per warp.
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int sub = (warp - 2) >> 2;              // which chunks of the tile (c0 = 32*sub, +128, ...)
+        const int et = threadIdx.x - 64;              // 0..kEpiThreads-1 within the epilogue group
+        int it = 0;
+        const uint32_t bar_tempty_leader = mapa_shared(bar_tempty, 0);
+        for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / p.n_tiles) * (2 * kBM) + static_cast<int>(cta_rank) * kBM;   // this CTA's 128 rows
+            const int n0 = (tile % p.n_tiles) * p.block_n;
+
+            // Stage this tile's bias slice in shared memory (double-buffered by tile parity; the
+            // single named barrier per tile also orders reuse of the other buffer).
+            float* bs = bias_s[it & 1];
+            if (et < p.block_n) {
+                const int n = n0 + et;
+                bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            float pos_v = 0.f;
+            if (p.pos != nullptr && row_ok) pos_v = __ldg(p.pos + (row % p.pos_period));
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>(acc * kMaxBN);
+
+            for (int c0 = sub * 32; c0 < p.block_n; c0 += 128) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c0, v);
+                tmem_ld_wait();
+                const bool full = n0 + c0 + 32 <= p.N;      // block_n is a multiple of 32: chunks are never partial in the tile
+                if (OUT_F32) {
+                    if (!row_ok) continue;
+                    float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc;
+                    const float* rrow = p.resid ? p.resid + static_cast<size_t>(row) * p.ldr : nullptr;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int c = c0 + 4 * g;
+                        const int n = n0 + c;
+                        if (full || n < p.n_store) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c);
+                            float x[4] = {__uint_as_float(v[4 * g + 0]) + b4.x, __uint_as_float(v[4 * g + 1]) + b4.y,
+                                          __uint_as_float(v[4 * g + 2]) + b4.z, __uint_as_float(v[4 * g + 3]) + b4.w};
+                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
+                            const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float y = apply_act<ACT, false>(x[j] + pos_v) + r[j];
+                                x[j] = (full || n + j < p.N) ? y : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
+                        }
+                    }
+                } else {
+                    // bf16 output: this warp's 32 x 32 sub-tile goes to its 64B-swizzled staging tile
+                    // (row = lane, 64 B per row; 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3),
+                    // which is both what CU_TENSOR_MAP_SWIZZLE_64B expects and bank-conflict free), then
+                    // one TMA store writes it with full 64-byte row segments.  Rows >= M and columns past
+                    // the tensor width are clipped by the TMA unit.
+                    const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp - 2) * kStoreTileBytes;
+                    uint32_t o[16];
+                    if (full) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 0]) + b4.x);
+                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 1]) + b4.y);
+                            const float y2 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 2]) + b4.z);
+                            const float y3 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 3]) + b4.w);
+                            o[2 * g] = pack_bf16x2(y0, y1);
+                            o[2 * g + 1] = pack_bf16x2(y2, y3);
+                        }
+                    } else {      // last N tile: columns >= N are written as zero
+#pragma unroll
+                        for (int g = 0; g < 16; ++g) {
+                            const int n = n0 + c0 + 2 * g;
+                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 0]) + bs[c0 + 2 * g]);
+                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 1]) + bs[c0 + 2 * g + 1]);
+                            o[g] = pack_bf16x2(n < p.N ? y0 : 0.f, n + 1 < p.N ? y1 : 0.f);
+                        }
+                    }
+                    // only now wait for the previous TMA store of this warp to have left the staging
+                    // tile: its read latency is hidden behind the arithmetic above
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t dst = s_tile + static_cast<uint32_t>(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * g]), "r"(o[4 * g + 1]),
+                                     "r"(o[4 * g + 2]), "r"(o[4 * g + 3]) : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, s_tile, n0 + c0, m0 + quad * 32);
+                        tma_store_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_tempty_leader + 8 * acc);
+        }
+        if (!OUT_F32 && lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();            // the leader's MMAs touch the peer's smem and TMEM: nobody leaves early
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+template <int ACT, bool OUT_F32>
+cudaError_t launch_variant2(const TcGemmPlan& plan, const Tc2GemmArgs& a, cudaStream_t stream) {
+    auto kern = gemm_tc2_kernel<ACT, OUT_F32>;
+    static bool attr_done = false;   // per template instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, plan.tmA, plan.tmB, plan.tmC, a);
+}
+
+}  // namespace
+
+// Plan for the CTA-pair kernel: tile = 256 rows x BN columns per cluster, W box = BN/2 rows per CTA.
+int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) return -2;
+    if ((d.lda % 8) || (d.ldw % 8)) return -3;
+    if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.W) & 15) ||
+        (reinterpret_cast<uintptr_t>(d.out) & 15))
+        return -4;
+    const int vec = d.out_f32 ? 4 : 8;
+    if ((d.ldc % vec) || d.ldc < (d.N + vec - 1) / vec * vec) return -5;
+    if (d.resid && (!d.out_f32 || (d.ldr % 4) || d.ldr < (d.N + 3) / 4 * 4)) return -6;
+    if (d.pos && !d.out_f32) return -8;
+    int bn = d.block_n > 0 ? d.block_n : choose_block_n(d.N);
+    if (bn % 32 || bn < 32 || bn > kMaxBN) return -7;
+
+    plan->desc = d;
+    plan->block_n = bn;
+    const int stage = kStageBytesA + (bn / 2) * kBK * 2;
+    int stages = kRingBytes / stage;
+    if (stages > kMaxStages) stages = kMaxStages;
+    plan->num_stages = stages;
+    plan->smem_bytes = kMaxDynSmem;
+    const int m_tiles = (d.M + 2 * kBM - 1) / (2 * kBM);
+    const int n_tiles = (d.N + bn - 1) / bn;
+    plan->n_tiles = n_tiles;
+    plan->num_tiles = m_tiles * n_tiles;
+    const int clusters = num_sms / 2;
+    plan->grid = 2 * (plan->num_tiles < clusters ? plan->num_tiles : clusters);
+    int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, d.K, d.lda, kBM);
+    if (r) return r;
+    r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, d.K, d.ldw, bn / 2);
+    if (r) return r;
+    if (!d.out_f32) r = make_tmap_bf16_2d_ex(&plan->tmC, d.out, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
+    else plan->tmC = plan->tmA;
+    return r;
+}
+
+cudaError_t tc2_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
+    const GemmDesc& d = plan.desc;
+    Tc2GemmArgs a;
+    a.M = d.M; a.N = d.N; a.K = d.K;
+    a.block_n = plan.block_n;
+    a.num_stages = plan.num_stages;
+    a.n_tiles = plan.n_tiles;
+    a.num_tiles = plan.num_tiles;
+    a.num_kb = (d.K + kBK - 1) / kBK;
+    a.bias = d.bias;
+    a.pos = d.pos;
+    a.pos_period = d.pos_period > 0 ? d.pos_period : 1;
+    a.resid = d.resid;
+    a.ldr = d.ldr;
+    a.out = d.out;
+    a.ldc = d.ldc;
+    a.n_store = d.out_f32 ? (d.N + 3) / 4 * 4 : (d.N + 7) / 8 * 8;
+    if (d.out_f32) {
+        switch (d.act) {
+            case ACT_NONE: return launch_variant2<ACT_NONE, true>(plan, a, stream);
+            case ACT_MISH: return launch_variant2<ACT_MISH, true>(plan, a, stream);
+            case ACT_GELU: return launch_variant2<ACT_GELU, true>(plan, a, stream);
+        }
+    } else {
+        switch (d.act) {
+            case ACT_NONE: return launch_variant2<ACT_NONE, false>(plan, a, stream);
+            case ACT_MISH: return launch_variant2<ACT_MISH, false>(plan, a, stream);
+            case ACT_GELU: return launch_variant2<ACT_GELU, false>(plan, a, stream);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace vitdet

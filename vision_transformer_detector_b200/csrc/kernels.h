@@ -43,6 +43,7 @@ struct TcGemmPlan {
     int num_tiles = 0;
     int grid = 0;
     size_t smem_bytes = 0;
+    int pair = 0;              // 1: built for the CTA-pair kernel
 };
 
 int choose_block_n(int N);
@@ -50,6 +51,9 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int cols, in
 int make_tmap_bf16_2d_ex(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows, int swizzle_bytes);
 int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms);
 cudaError_t tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
+// CTA-pair (cta_group::2) variant for the large layers (gemm_tc2.cu): 256 x BN tile per 2-CTA cluster.
+int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms);
+cudaError_t tc2_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
 
 // f32 CUDA-core GEMM with the same epilogue (the fp32 parity mode); A, W, out are f32.
 // Requires lda, ldw multiples of 4 and zero padding of A and W in columns [K, round_up(K,4)).
