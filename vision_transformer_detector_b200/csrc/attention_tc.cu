@@ -23,6 +23,7 @@
 // SFU idle (profiles/r01c_*).
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace vitdet {
 
@@ -62,6 +63,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     const int q0 = blockIdx.x * kQ;
     const int bh = blockIdx.y;
     const int b = bh / p.H, h = bh - b * p.H;
@@ -100,6 +102,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();       // set-up above overlapped the previous kernel; q/k/v are read from here on
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -304,8 +307,7 @@ cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream) {
         attr_done = true;
     }
     dim3 grid((d.T + kQ - 1) / kQ, d.B * d.H);
-    attn_tc_kernel<<<grid, kThreads, smem, stream>>>(plan.tmQKV, a);
-    return cudaGetLastError();
+    return launch_kernel(attn_tc_kernel, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
 }
 
 }  // namespace vitdet

@@ -68,6 +68,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (see launch.h)
+// ---------------------------------------------------------------------------------------------
+// Lets the next kernel of the stream start its prologue; call as early as possible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Returns when the predecessor grid has completed and its global writes are visible.  No-op without PDL.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // Shared-memory addresses, mbarriers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

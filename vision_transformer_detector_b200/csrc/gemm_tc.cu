@@ -22,6 +22,7 @@
 // binary serves every layer width of the model.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace vitdet {
 
@@ -72,6 +73,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0u) __trap();          // 128B-swizzled stages need 1024-byte alignment
@@ -109,6 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();       // set-up above overlapped the previous kernel; its outputs are read from here on
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -310,8 +313,7 @@ cudaError_t launch_variant(const TcGemmPlan& plan, const TcGemmArgs& a, cudaStre
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmA, plan.tmB, plan.tmC, a);
-    return cudaGetLastError();
+    return launch_kernel(kern, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, 1, plan.tmA, plan.tmB, plan.tmC, a);
 }
 
 }  // namespace

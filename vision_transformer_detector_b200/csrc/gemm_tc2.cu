@@ -15,6 +15,7 @@
 //               leader's barrier from both CTAs.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace vitdet {
 
@@ -65,6 +66,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0u) __trap();          // 128B-swizzled stages need 1024-byte alignment
@@ -104,6 +106,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();            // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();       // set-up above overlapped the previous kernel; its outputs are read from here on
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -287,19 +290,7 @@ cudaError_t launch_variant2(const TcGemmPlan& plan, const Tc2GemmArgs& a, cudaSt
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = plan.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, plan.tmA, plan.tmB, plan.tmC, a);
+    return launch_kernel(kern, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, 2, plan.tmA, plan.tmB, plan.tmC, a);
 }
 
 }  // namespace

@@ -4,6 +4,7 @@
 // warp-shuffle reductions, no shared-memory staging (there is no reuse to exploit).
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace vitdet {
 
@@ -77,6 +78,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int M, int D, float eps, T* __restrict__ y, int ldy) {
     constexpr int ROWS_PER_BLOCK = 256 / LPR;
+    pdl_launch_dependents();
+    pdl_wait();
     const int sub = threadIdx.x % LPR;
     const int row = blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / LPR;
     const bool row_ok = row < M;
@@ -143,6 +146,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                   const float* __restrict__ bias, long long total, int D, int S, T* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const long long m = idx / S;
@@ -229,6 +234,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_tail_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ w, const float* __restrict__ bias,
                  int R, int U, DecodeParams dp, DecodeOut o) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= R) return;
@@ -254,6 +261,8 @@ head_tail_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ w, 
 
 __global__ void __launch_bounds__(256)
 decode_kernel(const float* __restrict__ logits, int R, DecodeParams dp, DecodeOut o) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     float l[6];
@@ -271,13 +280,12 @@ cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b,
     const int grid = (M + rows_per_block - 1) / rows_per_block;
     const int width = ldy > D ? ldy : D;
     const int chunks = (width + 4 * LPR - 1) / (4 * LPR);
-    if (chunks <= 1) layernorm_kernel<LPR, 1, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
-    else if (chunks <= 2) layernorm_kernel<LPR, 2, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
-    else if (chunks <= 4) layernorm_kernel<LPR, 4, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
-    else if (chunks <= 8) layernorm_kernel<LPR, 8, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
-    else if (chunks <= 16) layernorm_kernel<LPR, 16, T><<<grid, 256, 0, st>>>(x, ldx, g, b, M, D, eps, y, ldy);
-    else return cudaErrorInvalidValue;   // embedding_dim > 2048 is outside what this build supports
-    return cudaGetLastError();
+    if (chunks <= 1) return launch_kernel(layernorm_kernel<LPR, 1, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 2) return launch_kernel(layernorm_kernel<LPR, 2, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 4) return launch_kernel(layernorm_kernel<LPR, 4, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 8) return launch_kernel(layernorm_kernel<LPR, 8, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 16) return launch_kernel(layernorm_kernel<LPR, 16, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    return cudaErrorInvalidValue;   // embedding_dim > 2048 is outside what this build supports
 }
 
 }  // namespace
@@ -289,12 +297,10 @@ cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, voi
     if (ldp < 3 * p * p) return cudaErrorInvalidValue;
     dim3 grid(gh * p, B);
     if (out_f32)
-        patchify_kernel<float><<<grid, 256, 0, stream>>>(images, H, W, p, gh, gw, pad_top, pad_left,
-                                                         static_cast<float*>(patches), ldp);
-    else
-        patchify_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(images, H, W, p, gh, gw, pad_top, pad_left,
-                                                                 static_cast<__nv_bfloat16*>(patches), ldp);
-    return cudaGetLastError();
+        return launch_kernel(patchify_kernel<float>, grid, dim3(256), 0, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left,
+                             static_cast<float*>(patches), ldp);
+    return launch_kernel(patchify_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, 1, images, H, W, p, gh, gw, pad_top,
+                         pad_left, static_cast<__nv_bfloat16*>(patches), ldp);
 }
 
 cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D, float eps,
@@ -314,28 +320,25 @@ cudaError_t head_slots_launch(const float* x, int ldx, const float* w, const flo
     const long long total = static_cast<long long>(M) * S;
     const int grid = static_cast<int>((total + 255) / 256);
     if (out_f32)
-        head_slots_kernel<float><<<grid, 256, 0, stream>>>(x, ldx, w, bias, total, D, S, static_cast<float*>(out));
-    else
-        head_slots_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, ldx, w, bias, total, D, S,
-                                                                   static_cast<__nv_bfloat16*>(out));
-    return cudaGetLastError();
+        return launch_kernel(head_slots_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S,
+                             static_cast<float*>(out));
+    return launch_kernel(head_slots_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S,
+                         static_cast<__nv_bfloat16*>(out));
 }
 
 cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w, const float* bias, int R, int U,
                              const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream) {
     const int grid = (R * 32 + 255) / 256;
     if (in_f32)
-        head_tail_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(h), ldh, w, bias, R, U, dp, out);
-    else
-        head_tail_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), ldh, w, bias,
-                                                                  R, U, dp, out);
-    return cudaGetLastError();
+        return launch_kernel(head_tail_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(h), ldh, w,
+                             bias, R, U, dp, out);
+    return launch_kernel(head_tail_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1,
+                         static_cast<const __nv_bfloat16*>(h), ldh, w, bias, R, U, dp, out);
 }
 
 cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,
                           cudaStream_t stream) {
-    decode_kernel<<<(R + 255) / 256, 256, 0, stream>>>(logits, R, dp, out);
-    return cudaGetLastError();
+    return launch_kernel(decode_kernel, dim3((R + 255) / 256), dim3(256), 0, stream, 1, logits, R, dp, out);
 }
 
 }  // namespace vitdet
