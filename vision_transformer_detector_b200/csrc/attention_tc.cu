@@ -55,6 +55,90 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
+// One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that
+// hold at least one existing key (4 for a full tile), MASK = the last of them is partial.  Static loops only,
+// so that the 128 scores stay in registers.
+template <int NCH, bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t tO, uint32_t bar_s_free, uint32_t bar_pv_done,
+                                             uint32_t bar_p_full, int lane, int j, int valid, float scale_log2,
+                                             float& m_used, float& l) {
+    // the row slice into registers (all loads in flight, one wait), then S belongs to the MMA warp again and
+    // QK^T(j+1) overlaps this tile's softmax
+    uint32_t v[NCH][32];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tS + 32u * c, v[c]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_s_free);
+
+    if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (32 * (NCH - 1) + i >= valid) v[NCH - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
+    }
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
+            mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
+        }
+    const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2);
+    const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile
+    float alpha = 1.f;
+    if (grow) {
+        alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
+        m_used = m_new;
+        l *= alpha;
+    }
+    const float neg_m = -m_used;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float e0 = ex2f(fmaf(__uint_as_float(v[c][i]), scale_log2, neg_m));      // ex2(-inf) = 0
+            const float e1 = ex2f(fmaf(__uint_as_float(v[c][i + 1]), scale_log2, neg_m));
+            const float e2 = ex2f(fmaf(__uint_as_float(v[c][i + 2]), scale_log2, neg_m));
+            const float e3 = ex2f(fmaf(__uint_as_float(v[c][i + 3]), scale_log2, neg_m));
+            sum[0] += e0; sum[1] += e1; sum[2] += e2; sum[3] += e3;
+            v[c][i / 2] = pack_bf16x2(e0, e1);
+            v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
+        }
+    l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+
+    // P and O must no longer be in use by PV(j-1)
+    if (j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (grow) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(tO + 32u * c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32_x32(tO + 32u * c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = (c < NCH) ? v[c < NCH ? c : 0][i] : 0u;     // P = 0 for keys that do not exist
+        tmem_st_32x32_x16(tP + 16u * c, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p_full);
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -168,91 +252,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         const uint32_t tP = tmem_base + lane_off + kColP, tO = tmem_base + lane_off + kColO;
         float m_used = -INFINITY;      // running maximum in the scaled log2 domain
         float l = 0.f;                 // running sum of p
+        const uint32_t tS = tmem_base + lane_off + kColS;
         for (int j = 0; j < nkv; ++j) {
             const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
-            const uint32_t tS = tmem_base + lane_off + kColS;
             mbar_wait(bar_s_full, j & 1);
             tc_fence_after();
-
-            // the whole row slice into registers (four loads in flight, one wait), then S belongs to the
-            // MMA warp again and QK^T(j+1) overlaps this tile's softmax
-            uint32_t v[4][32];
-            tmem_ld_32x32(tS, v[0]);
-            tmem_ld_32x32(tS + 32u, v[1]);
-            tmem_ld_32x32(tS + 64u, v[2]);
-            tmem_ld_32x32(tS + 96u, v[3]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_s_free);
-
-            if (valid < kKV) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (32 * c + i >= valid) v[c][i] = 0xff800000u;     // -inf: keys past the end of the image
-            }
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
-                    mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
-                }
-            const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2);
-            const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile
-            float alpha = 1.f;
-            if (grow) {
-                alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
-                m_used = m_new;
-                l *= alpha;
-            }
-            const float neg_m = -m_used;
-            float sum[4] = {0.f, 0.f, 0.f, 0.f};
-            // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float e0 = ex2f(fmaf(__uint_as_float(v[c][i]), p.scale_log2, neg_m));      // ex2(-inf) = 0
-                    const float e1 = ex2f(fmaf(__uint_as_float(v[c][i + 1]), p.scale_log2, neg_m));
-                    const float e2 = ex2f(fmaf(__uint_as_float(v[c][i + 2]), p.scale_log2, neg_m));
-                    const float e3 = ex2f(fmaf(__uint_as_float(v[c][i + 3]), p.scale_log2, neg_m));
-                    sum[0] += e0; sum[1] += e1; sum[2] += e2; sum[3] += e3;
-                    v[c][i / 2] = pack_bf16x2(e0, e1);
-                    v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
-                }
-            l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
-
-            // P and O must no longer be in use by PV(j-1)
-            if (j > 0) {
-                mbar_wait(bar_pv_done, (j - 1) & 1);
-                tc_fence_after();
-                if (grow) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t o[32];
-                        tmem_ld_32x32(tO + 32u * c, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32_x32(tO + 32u * c, o);
-                    }
+#define VITDET_TILE(NCH, MASK) \
+    softmax_tile<NCH, MASK>(tS, tP, tO, bar_s_free, bar_pv_done, bar_p_full, lane, j, valid, p.scale_log2, m_used, l)
+            if (valid == kKV) {
+                VITDET_TILE(4, false);
+            } else {
+                // last tile of the image: only the chunks with existing keys are loaded and exponentiated
+                // (16 of 128 keys at T = 1296); warp-uniform dispatch
+                const bool partial = (valid & 31) != 0;
+                switch ((valid + 31) >> 5) {
+                    case 1: if (partial) VITDET_TILE(1, true); else VITDET_TILE(1, false); break;
+                    case 2: if (partial) VITDET_TILE(2, true); else VITDET_TILE(2, false); break;
+                    case 3: if (partial) VITDET_TILE(3, true); else VITDET_TILE(3, false); break;
+                    default: VITDET_TILE(4, true); break;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = v[c][i];
-                tmem_st_32x32_x16(tP + 16u * c, pk);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_p_full);
+#undef VITDET_TILE
         }
 
         // ---- finalise: O / l -> bf16 context rows ----
