@@ -56,13 +56,12 @@ struct Tc2GemmArgs {
 };
 
 template <int ACT, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)   // 96 registers is the most 576 threads can be granted (104 and 112 fail to launch)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Tc2GemmArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float bias_s[2][kMaxBN];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -161,7 +160,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // 32-column chunks round-robin (sub = 0..3), so a 256-wide tile is two chunks per warp.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int sub = (warp - 2) >> 2;              // which chunks of the tile (c0 = 32*sub, +128, ...)
-        const int et = threadIdx.x - 64;              // 0..kEpiThreads-1 within the epilogue group
         int it = 0;
         const uint32_t bar_tempty_leader = mapa_shared(bar_tempty, 0);
         for (int tile = blockIdx.x >> 1; tile < p.num_tiles; tile += gridDim.x >> 1, ++it) {
@@ -170,15 +168,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int m0 = (tile / p.n_tiles) * (2 * kBM) + static_cast<int>(cta_rank) * kBM;   // this CTA's 128 rows
             const int n0 = (tile % p.n_tiles) * p.block_n;
 
-            // Stage this tile's bias slice in shared memory (double-buffered by tile parity; the
-            // single named barrier per tile also orders reuse of the other buffer).
-            float* bs = bias_s[it & 1];
-            if (et < p.block_n) {
-                const int n = n0 + et;
-                bs[et] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-
+            // Bias is read straight from global memory below (a warp-wide broadcast that stays in L1): no staging
+            // barrier per tile, so the sixteen epilogue warps drift apart and their SFU phases interleave.
+            const float* bs = p.bias + n0;      // valid for columns < N only; the tail path guards its reads
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
 
@@ -203,7 +195,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const int c = c0 + 4 * g;
                         const int n = n0 + c;
                         if (full || n < p.n_store) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c);
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr) {
+                                if (full) b4 = __ldg(reinterpret_cast<const float4*>(bs + c));
+                                else {
+                                    b4.x = (n + 0 < p.N) ? __ldg(bs + c + 0) : 0.f; b4.y = (n + 1 < p.N) ? __ldg(bs + c + 1) : 0.f;
+                                    b4.z = (n + 2 < p.N) ? __ldg(bs + c + 2) : 0.f; b4.w = (n + 3 < p.N) ? __ldg(bs + c + 3) : 0.f;
+                                }
+                            }
                             float x[4] = {__uint_as_float(v[4 * g + 0]) + b4.x, __uint_as_float(v[4 * g + 1]) + b4.y,
                                           __uint_as_float(v[4 * g + 2]) + b4.z, __uint_as_float(v[4 * g + 3]) + b4.w};
                             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -228,7 +227,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (full) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bs + c0 + 4 * g);
+                            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
                             const float y0 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 0]) + b4.x);
                             const float y1 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 1]) + b4.y);
                             const float y2 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 2]) + b4.z);
@@ -240,8 +239,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int g = 0; g < 16; ++g) {
                             const int n = n0 + c0 + 2 * g;
-                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 0]) + bs[c0 + 2 * g]);
-                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 1]) + bs[c0 + 2 * g + 1]);
+                            const float bb0 = (p.bias && n < p.N) ? __ldg(bs + c0 + 2 * g) : 0.f;
+                            const float bb1 = (p.bias && n + 1 < p.N) ? __ldg(bs + c0 + 2 * g + 1) : 0.f;
+                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 0]) + bb0);
+                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[2 * g + 1]) + bb1);
                             o[g] = pack_bf16x2(n < p.N ? y0 : 0.f, n + 1 < p.N ? y1 : 0.f);
                         }
                     }
