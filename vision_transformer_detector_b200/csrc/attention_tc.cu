@@ -4,13 +4,13 @@
 //
 // One CTA = 128 queries of one (image, head); two CTAs are resident per SM so that the softmax of one
 // overlaps the softmax latencies of the other.  192 threads:
-//   warp 0      TMA producer: Q once, then 128-key K and V tiles (cp.async.bulk.tensor, 128B swizzle)
+//   warp 4      TMA producer: Q once, then 128-key K and V tiles (cp.async.bulk.tensor, 128B swizzle)
 //               through a 3-stage mbarrier ring.
-//   warp 1      allocates 256 TMEM columns; one lane issues
+//   warp 5      allocates 256 TMEM columns; one lane issues
 //                 S = Q K(j)^T        tcgen05.mma  M128 x N128 x K(16*ceil(d/16)), A and B K-major from smem
 //                 O += P V(j)         tcgen05.mma  M128 x N64 x K128, A = P from TENSOR MEMORY, B = V MN-major
 //               QK^T(j+1) is issued as soon as the softmax warps have S(j) in registers.
-//   warps 2..5  softmax: thread = query row (TMEM lane).  One tcgen05.ld pass brings the 128 scores of
+//   warps 0..3  softmax: thread = query row (TMEM lane).  One tcgen05.ld pass brings the 128 scores of
 //               the row into registers (S is released to the MMA warp immediately), row maximum without
 //               shuffles, p = ex2(s*c - m), row sum, P written back to TMEM as packed bf16 (tcgen05.st) —
 //               never through shared memory.  The running maximum is only advanced (and O rescaled in
@@ -34,6 +34,9 @@ constexpr int kKV = 128;           // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kHP = 64;            // head pitch in elements (one 128-byte swizzle row of bf16)
 constexpr int kStages = 3;
 constexpr int kThreads = 192;
+// softmax warps 0..3 (warp = TMEM lane quadrant); the TMA producer and the MMA issuer take the highest warp ids,
+// which the warp arbiter favours: the MMA issuer's wake-up latency is on the critical path of every tile
+constexpr int kProducerWarp = 4, kMmaWarp = 5;
 constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
 constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one K tile or one V tile = two TMA boxes of 64 rows
 constexpr int kBoxBytes = 64 * kHP * 2;
@@ -178,7 +181,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         mbar_init(bar_pv_done, 1);
         fence_mbar_init();
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tmem_alloc(smem_u32(&tmem_base_s), kTmemCols);
         tmem_relinquish();
     }
@@ -188,7 +191,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     const uint32_t tmem_base = tmem_base_s;
     pdl_wait();       // set-up above overlapped the previous kernel; q/k/v are read from here on
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&tmQKV);
@@ -209,7 +212,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------ MMA issuer --------------------------------
         if (lane == 0) {
             const uint32_t idesc_qk = umma_idesc_bf16_f32(kQ, kKV);
@@ -302,7 +305,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
