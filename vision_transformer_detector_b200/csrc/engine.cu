@@ -446,6 +446,8 @@ struct DenseCall {
     const float* resid = nullptr; int ldr = 0;
     void* out; int ldc; int out_f32; int act;
     int M;
+    // optional fused LayerNorm of the output row (bf16 mode, N <= 32): see GemmDesc
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr; void* ln_out = nullptr; int ln_ld = 0; float ln_eps = 1e-3f;
 };
 
 static GemmDesc make_desc(const DenseCall& c, int mode) {
@@ -458,6 +460,7 @@ static GemmDesc make_desc(const DenseCall& c, int mode) {
     g.pos = c.pos; g.pos_period = c.pos_period;
     g.resid = c.resid; g.ldr = c.ldr;
     g.out = c.out; g.ldc = c.ldc; g.out_f32 = c.out_f32; g.act = c.act;
+    g.ln_gamma = c.ln_gamma; g.ln_beta = c.ln_beta; g.ln_out = c.ln_out; g.ln_ld = c.ln_ld; g.ln_eps = c.ln_eps;
     return g;
 }
 
@@ -476,6 +479,13 @@ static bool use_pair_kernel(int M, int N, int K) {
 static int make_tc_plan(TcGemmPlan* plan, const GemmDesc& g, int num_sms) {
     plan->pair = use_pair_kernel(g.M, g.N, g.K) ? 1 : 0;
     return plan->pair ? tc2_gemm_make_plan(plan, g, num_sms) : tc_gemm_make_plan(plan, g, num_sms);
+}
+
+// VITDET_FUSE_LN=0 keeps the stand-alone LayerNorm kernel (A/B measurements).
+static bool ln_is_fused(const vitdet_handle* h) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITDET_FUSE_LN"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+    return v == 1 && h->D <= 32;
 }
 
 static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
@@ -566,8 +576,15 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
     const int L = c.repeat_times, q = c.mlp_quantities;
     float* xdummy = h->x.as<float>();
 
+    // In bf16 mode with D <= 32 every LayerNorm is fused into the epilogue of the GEMM that produces the residual
+    // stream row (projection -> LN1 of block 0; attention output -> LN2; last MLP layer -> LN1 of the next block).
+    const bool fuse_ln = ln_is_fused(h);
+    auto with_ln = [&](DenseCall c, DevBuf& gamma, DevBuf& beta) {
+        if (fuse_ln) { c.ln_gamma = gamma.as<float>(); c.ln_beta = beta.as<float>(); c.ln_out = h->y.p; c.ln_ld = m.D8; c.ln_eps = h->cfg.ln_epsilon; }
+        return c;
+    };
     DenseCall pc{h->patch.p, m.Pld, &h->proj, h->pos.as<float>(), h->T, nullptr, 0, xdummy, m.D4, 1, ACT_NONE, Mc};
-    RC_TRY(plan_dense(h, pc, &ep->proj));
+    RC_TRY(plan_dense(h, with_ln(pc, h->blocks[0].ln1_g, h->blocks[0].ln1_b), &ep->proj));
 
     ep->qkv.resize(L); ep->out.resize(L); ep->attn.resize(L); ep->mlp.assign(L, std::vector<TcGemmPlan>(q));
     for (int i = 0; i < L; ++i) {
@@ -581,13 +598,14 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
         int rc = attn_bf16_make_plan(&ep->attn[i], ad);
         if (rc) return fail(VITDET_E_INVALID, "attn_bf16_make_plan failed: %d", rc);
         DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, xdummy, m.D4, xdummy, m.D4, 1, ACT_NONE, Mc};
-        RC_TRY(plan_dense(h, oc, &ep->out[i]));
+        RC_TRY(plan_dense(h, with_ln(oc, b.ln2_g, b.ln2_b), &ep->out[i]));
         const void* a = h->y.p; int lda = m.D8;
         for (int j = 0; j < q; ++j) {
             const bool last = j == q - 1;
             void* o = last ? static_cast<void*>(xdummy) : ((j & 1) ? h->u1.p : h->u0.p);
             const int ldo = last ? m.D4 : round_up(b.mlp[j].N, 8);
             DenseCall mc{a, lda, &b.mlp[j], nullptr, 1, last ? xdummy : nullptr, last ? m.D4 : 0, o, ldo, last ? 1 : 0, h->act, Mc};
+            if (last && i + 1 < L) mc = with_ln(mc, h->blocks[i + 1].ln1_g, h->blocks[i + 1].ln1_b);
             RC_TRY(plan_dense(h, mc, &ep->mlp[i][j]));
             a = o; lda = ldo;
         }
@@ -726,7 +744,7 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
         for (int i = 0; i < L; ++i) {
             BlockW& b = h->blocks[i];
             const int ldy = bf ? m.D8 : m.D4;
-            { ProfScope ps(h, PC_LN, st);
+            if (!(bf && ln_is_fused(h))) { ProfScope ps(h, PC_LN, st);
             CU_TRY(layernorm_launch(x, m.D4, b.ln1_g.as<float>(), b.ln1_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
             if (bf) {
                 { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_tc(ep->qkv[i], h->qkv.p, nullptr, st)); }
@@ -743,7 +761,7 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
                 DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, x, m.D4, x, m.D4, 1, ACT_NONE, Mc};
                 { ProfScope ps(h, PC_OUT, st); RC_TRY(launch_simt(oc, st)); }
             }
-            { ProfScope ps(h, PC_LN, st);
+            if (!(bf && ln_is_fused(h))) { ProfScope ps(h, PC_LN, st);
             CU_TRY(layernorm_launch(x, m.D4, b.ln2_g.as<float>(), b.ln2_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
             const void* a = h->y.p; int lda = ldy;
             for (int j = 0; j < q; ++j) {

@@ -64,6 +64,11 @@ struct TcGemmArgs {
     void* out;
     int ldc;
     int n_store;   // round_up(N, store vector): columns [N, n_store) are written as zero
+    const float* ln_gamma;      // fused LayerNorm of the output row (f32 output, N <= 32), or nullptr
+    const float* ln_beta;
+    float ln_eps;
+    __nv_bfloat16* ln_out;
+    int ln_ld;
 };
 
 template <int ACT, bool OUT_F32>
@@ -199,10 +204,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (!row_ok) continue;
                     float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc;
                     const float* rrow = p.resid ? p.resid + static_cast<size_t>(row) * p.ldr : nullptr;
+                    float xr[32];        // the finished values of this chunk (kept for the fused LayerNorm)
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const int c = c0 + 4 * g;
                         const int n = n0 + c;
+                        float x[4] = {0.f, 0.f, 0.f, 0.f};
                         if (full || n < p.n_store) {
                             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p.bias != nullptr) {
@@ -212,8 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     b4.z = (n + 2 < p.N) ? __ldg(bs + c + 2) : 0.f; b4.w = (n + 3 < p.N) ? __ldg(bs + c + 3) : 0.f;
                                 }
                             }
-                            float x[4] = {__uint_as_float(v[4 * g + 0]) + b4.x, __uint_as_float(v[4 * g + 1]) + b4.y,
-                                          __uint_as_float(v[4 * g + 2]) + b4.z, __uint_as_float(v[4 * g + 3]) + b4.w};
+                            x[0] = __uint_as_float(v[4 * g + 0]) + b4.x; x[1] = __uint_as_float(v[4 * g + 1]) + b4.y;
+                            x[2] = __uint_as_float(v[4 * g + 2]) + b4.z; x[3] = __uint_as_float(v[4 * g + 3]) + b4.w;
                             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
                             const float r[4] = {r4.x, r4.y, r4.z, r4.w};
@@ -223,6 +230,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 x[j] = (full || n + j < p.N) ? y : 0.f;
                             }
                             *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xr[4 * g + j] = x[j];
+                    }
+                    if (p.ln_out != nullptr) {
+                        // keras LayerNormalization(axis=-1) of the row just produced (the host only sets ln_out when
+                        // the whole row is this one chunk): biased variance, eps inside the rsqrt, f32 statistics
+                        const float inv_n = 1.f / static_cast<float>(p.N);
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum += xr[i];                 // columns >= N are zero
+                        const float mean = sum * inv_n;
+                        float sq = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { const float dv = (i < p.N) ? xr[i] - mean : 0.f; sq = fmaf(dv, dv, sq); }
+                        const float rstd = rsqrtf(sq * inv_n + p.ln_eps);
+                        __nv_bfloat16* yrow = p.ln_out + static_cast<size_t>(row) * p.ln_ld;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (8 * g < p.ln_ld) {
+                                float o8[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int i = 8 * g + j;
+                                    o8[j] = (i < p.N) ? (xr[i] - mean) * rstd * __ldg(p.ln_gamma + i) + __ldg(p.ln_beta + i) : 0.f;
+                                }
+                                uint4 w;
+                                w.x = pack_bf16x2(o8[0], o8[1]); w.y = pack_bf16x2(o8[2], o8[3]);
+                                w.z = pack_bf16x2(o8[4], o8[5]); w.w = pack_bf16x2(o8[6], o8[7]);
+                                *reinterpret_cast<uint4*>(yrow + 8 * g) = w;
+                            }
                         }
                     }
                 } else {
@@ -371,6 +409,9 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     if ((d.ldc % vec) || d.ldc < (d.N + vec - 1) / vec * vec) return -5;
     if (d.resid && (!d.out_f32 || (d.ldr % 4) || d.ldr < (d.N + 3) / 4 * 4)) return -6;
     if (d.pos && !d.out_f32) return -8;      // the position scalar is only fused into f32-output layers
+    if (d.ln_out && (!d.out_f32 || d.N > 32 || !d.ln_gamma || !d.ln_beta || (d.ln_ld % 8) || d.ln_ld < (d.N + 7) / 8 * 8 || d.ln_ld > 32 ||
+                     (reinterpret_cast<uintptr_t>(d.ln_out) & 15)))
+        return -9;                            // fused LayerNorm needs the whole row in one 32-column chunk
     int bn = d.block_n > 0 ? d.block_n : choose_block_n(d.N);
     if (bn % 32 || bn < 32 || bn > kMaxBN) return -7;
 
@@ -416,6 +457,8 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
     a.out = d.out;
     a.ldc = d.ldc;
     a.n_store = d.out_f32 ? (d.N + 3) / 4 * 4 : (d.N + 7) / 8 * 8;
+    a.ln_gamma = d.ln_gamma; a.ln_beta = d.ln_beta; a.ln_eps = d.ln_eps;
+    a.ln_out = static_cast<__nv_bfloat16*>(d.ln_out); a.ln_ld = d.ln_ld;
     if (d.out_f32) {
         switch (d.act) {
             case ACT_NONE: return launch_variant<ACT_NONE, true>(plan, a, stream);

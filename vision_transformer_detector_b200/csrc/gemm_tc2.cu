@@ -311,6 +311,7 @@ int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     if ((d.ldc % vec) || d.ldc < (d.N + vec - 1) / vec * vec) return -5;
     if (d.resid && (!d.out_f32 || (d.ldr % 4) || d.ldr < (d.N + 3) / 4 * 4)) return -6;
     if (d.pos && !d.out_f32) return -8;
+    if (d.ln_out) return -9;       // the fused LayerNorm exists in the single-CTA kernel only (N <= 32 layers)
     int bn = d.block_n > 0 ? d.block_n : choose_block_n(d.N);
     if (bn % 32 || bn < 32 || bn > kMaxBN) return -7;
 

@@ -31,6 +31,13 @@ struct GemmDesc {
     int out_f32 = 0;
     int act = 0;               // vitdet::Act
     int block_n = 0;           // 0 = choose
+    // Optional fused LayerNormalization of the OUTPUT row (tensor-core kernel, f32 output, N <= 32 only: the
+    // epilogue thread holds the whole row): ln_out[m, :] = LN(out[m, :]) * gamma + beta as bf16, pads zero.
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    float ln_eps = 1e-3f;
+    void* ln_out = nullptr;    // bf16 [M, ln_ld]
+    int ln_ld = 0;
 };
 
 struct TcGemmPlan {
