@@ -244,6 +244,7 @@ struct vitdet_handle {
     int device = 0;
     int num_sms = 148;
     int gh = 0, gw = 0, T = 0, P = 0, D = 0, H = 0, d = 0, S = 0;
+    int RP = 0, PK = 0;                 // run pitch of one patch row (round_up(3p, 4)) and padded patch vector p * RP
     int act = ACT_MISH;
     int chunk = 64;
 
@@ -355,8 +356,14 @@ static int build_weight_table(vitdet_handle* h) {
 
     // transformer_preprocessor: Dense 'linear_projection' (det.py:297) then PositionEncoding's
     // Embedding(T, 1) 'position_encoding/position_embedding' (det.py:148-151, 291-293).
-    RC_TRY(h->proj.alloc(D, P));
+    // The patch vector is stored with every patch-row run padded from 3p to RP elements (patchify_kernel), so
+    // the kernel's K axis is scattered the same way: source row k -> column (k / 3p) * RP + k % 3p, pads zero.
+    RC_TRY(h->proj.alloc(D, h->PK));
     add_dense_slots(h, "linear_projection", &h->proj, P, D);
+    {
+        WeightSlot& ks = h->slots[h->slot_index["linear_projection/kernel"]];
+        ks.gk = 3 * c.patch_size; ks.pk = h->RP;
+    }
     { const int64_t shp[2] = {T, 1}; RC_TRY(add_vec_slot(h, "position_encoding/position_embedding/embeddings", &h->pos, 2, shp)); }
 
     h->blocks.resize(c.repeat_times);
@@ -509,7 +516,7 @@ static Dims dims_for(const vitdet_handle* h, int mode) {
     m.es = mode == VITDET_MODE_BF16 ? 2 : 4;
     m.D4 = round_up(h->D, 4);
     m.D8 = round_up(h->D, 8);
-    m.Pld = round_up(h->P, 8);
+    m.Pld = round_up(h->PK, 8);
     m.w_qkv = 3 * h->H * kHeadPitch;
     m.w_ctx = h->H * kHeadPitch;
     // MLP ping-pong: layer j writes buffer j & 1; widest even / odd layer outputs.
@@ -732,13 +739,13 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
         }
         const float* img = images + static_cast<size_t>(c0) * c.image_h * c.image_w * 3;
         { ProfScope ps(h, PC_PATCHIFY, st);
-        CU_TRY(patchify_launch(img, bc, c.image_h, c.image_w, c.patch_size, h->patch.p, bf ? m.Pld : round_up(h->P, 4), out_f32_act, st)); }
+        CU_TRY(patchify_launch(img, bc, c.image_h, c.image_w, c.patch_size, h->patch.p, bf ? m.Pld : round_up(h->PK, 4), h->RP, out_f32_act, st)); }
         if (bf) {
             ProfScope ps(h, PC_PROJ, st);
             RC_TRY(launch_tc(ep->proj, x, nullptr, st));
         } else {
             ProfScope ps(h, PC_PROJ, st);
-            DenseCall pc{h->patch.p, round_up(h->P, 4), &h->proj, h->pos.as<float>(), T, nullptr, 0, x, m.D4, 1, ACT_NONE, Mc};
+            DenseCall pc{h->patch.p, round_up(h->PK, 4), &h->proj, h->pos.as<float>(), T, nullptr, 0, x, m.D4, 1, ACT_NONE, Mc};
             RC_TRY(launch_simt(pc, st));
         }
         for (int i = 0; i < L; ++i) {
@@ -874,6 +881,8 @@ int vitdet_create(const vitdet_config* cfg, vitdet_handle** out) {
     h->gw = (c.image_w + c.patch_size - 1) / c.patch_size;
     h->T = h->gh * h->gw;
     h->P = 3 * c.patch_size * c.patch_size;
+    h->RP = round_up(3 * c.patch_size, 4);
+    h->PK = c.patch_size * h->RP;
     h->D = c.embedding_dim; h->H = c.num_heads; h->d = c.key_dim; h->S = c.num_slots;
     h->act = c.use_mish ? ACT_MISH : ACT_GELU;
     int rc = build_weight_table(h);
@@ -1228,7 +1237,7 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
 
 int vitdet_op_patchify(const float* images, int B, int H, int W, int p, float* patches, void* stream) {
     if (!images || !patches || B <= 0 || H <= 0 || W <= 0 || p <= 0) return fail(VITDET_E_INVALID, "op_patchify: bad arguments");
-    CU_TRY(patchify_launch(images, B, H, W, p, patches, 3 * p * p, 1, static_cast<cudaStream_t>(stream)));
+    CU_TRY(patchify_launch(images, B, H, W, p, patches, 3 * p * p, 3 * p, 1, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

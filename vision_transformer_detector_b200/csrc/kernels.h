@@ -91,8 +91,9 @@ cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 // Memory-bound row kernels
 // ------------------------------------------------------------------------------------------------
 // tf.image.extract_patches(sizes=strides=p, padding='SAME') + Reshape (det.py:195-197, 279-280).
-// images f32 NHWC [B,H,W,3] -> patches [B*gh*gw, ldp] (element (r*p + c)*3 + ch), zero padded.
-cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp,
+// images f32 NHWC [B,H,W,3] -> patches [B*gh*gw, ldp]: element r*rp + c*3 + ch (rp >= 3p = run pitch of one
+// patch row; rp = 3p is the reference's dense vector), zero padded.
+cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int rp,
                             int out_f32, cudaStream_t stream);
 
 // keras LayerNormalization(axis=-1), eps=1e-3, biased variance (det.py:353-357, 375-379).

@@ -32,37 +32,75 @@ template <> struct OutT<__nv_bfloat16> {
 // (det.py:195-197) followed by Reshape((-1, 3p^2)) (det.py:279-280):
 //   grid = ceil(H/p) x ceil(W/p); pad_total = grid*p - size, pad_before = pad_total / 2, zeros;
 //   patch vector element (r*p + c)*3 + ch; tokens row-major over the grid.
-// One block per (image, padded image row): reads one contiguous image row, writes gw runs of 3p
-// elements.  Blocks with r == 0 also clear the pad columns [3p^2, ldp) of their gw tokens.
+// Output layout: token row = p runs (one per patch row r) of `rp` elements, rp >= 3p; elements [3p, rp) of a
+// run and [p*rp, ldp) of a token row are zero.  The engine uses rp = round_up(3p, 4) (52 for p = 17) so that
+// every run starts 8-byte aligned and is written with 4-element vector stores (the projection weight is
+// packed with the same zero columns); rp = 3p gives the reference's dense 3p^2 vector.
+// One block per (image, token row of the grid).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T> struct Vec4Store;
+template <> struct Vec4Store<float> {
+    static __device__ __forceinline__ void st(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <> struct Vec4Store<__nv_bfloat16> {
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float a, float b, float c, float d) {
+        uint2 o;
+        o.x = pack_bf16x2(a, b);
+        o.y = pack_bf16x2(c, d);
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+};
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, int H, int W, int p, int gh, int gw, int pad_top,
-                int pad_left, T* __restrict__ out, int ldp) {
-    const int yy = blockIdx.x;          // padded row index in [0, gh*p)
+                int pad_left, T* __restrict__ out, int ldp, int rp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int py = blockIdx.x;          // token row of the patch grid
     const int b = blockIdx.y;
-    const int py = yy / p, r = yy - py * p;
-    const int y = yy - pad_top;
-    const int run = 3 * p;              // contiguous elements per (token, r)
-    const int row_elems = gw * run;
-    const bool y_ok = (y >= 0) && (y < H);
-    const float* src = img + (static_cast<size_t>(b) * H + (y_ok ? y : 0)) * W * 3;
+    const int run = 3 * p;              // source elements per (token, r)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t tok0 = (static_cast<size_t>(b) * gh + py) * gw;
-    const int P = run * p;
-    for (int e = threadIdx.x; e < row_elems; e += blockDim.x) {
-        const int px = e / run;
-        const int within = e - px * run;
-        const int x3 = e - 3 * pad_left;
-        float v = 0.f;
-        if (y_ok && x3 >= 0 && x3 < 3 * W) v = __ldg(src + x3);
-        OutT<T>::st(out + (tok0 + px) * ldp + r * run + within, v);
-    }
-    if (r == 0 && ldp > P) {
-        const int padw = ldp - P;
-        for (int e = threadIdx.x; e < gw * padw; e += blockDim.x) {
-            const int px = e / padw;
-            OutT<T>::st(out + (tok0 + px) * ldp + P + (e - px * padw), 0.f);
+    const int W3 = 3 * W;
+    // No integer divisions and no staging: 16 or 32 lanes take one (token, r) run of 3p source floats, the
+    // warps stride over the tokens, r is the (uniform) outer loop.  Consecutive tokens read consecutive
+    // source bytes, so the misaligned scalar loads hit L1 after the first touch of each sector.
+    const int gpr = VEC ? (rp >> 2) : rp;                  // store groups per run (4 elements or 1)
+    const int lpr_shift = (VEC && gpr <= 16) ? 4 : 5;      // lanes per run: 16 or 32
+    const int runs_per_warp = 32 >> lpr_shift;
+    const int sub = lane >> lpr_shift, q0 = lane & ((1 << lpr_shift) - 1);
+    for (int r = 0; r < p; ++r) {
+        const int y = py * p + r - pad_top;
+        const bool y_ok = (y >= 0) && (y < H);
+        const float* src = img + (static_cast<size_t>(b) * H + (y_ok ? y : 0)) * W3 - 3 * pad_left;
+        for (int px = warp * runs_per_warp + sub; px < gw; px += 8 * runs_per_warp) {
+            T* dst = out + (tok0 + px) * ldp + r * rp;
+            const int x0 = px * run;                       // index into the padded row; source index = x0 + w - 3*pad_left
+            for (int q = q0; q < gpr; q += (1 << lpr_shift)) {
+                if (VEC) {
+                    const int w = 4 * q;
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int x3 = x0 + w + j - 3 * pad_left;
+                        v[j] = (y_ok && w + j < run && x3 >= 0 && x3 < W3) ? __ldg(src + x0 + w + j) : 0.f;
+                    }
+                    Vec4Store<T>::st(dst + w, v[0], v[1], v[2], v[3]);
+                } else {
+                    const int x3 = x0 + q - 3 * pad_left;
+                    OutT<T>::st(dst + q, (y_ok && q < run && x3 >= 0 && x3 < W3) ? __ldg(src + x0 + q) : 0.f);
+                }
+            }
         }
+    }
+    const int P = rp * p;
+    if (ldp > P) {
+        const int padw = ldp - P;
+        for (int px = warp; px < gw; px += 8)
+            for (int w = lane; w < padw; w += 32) OutT<T>::st(out + (tok0 + px) * ldp + P + w, 0.f);
     }
 }
 
@@ -290,17 +328,23 @@ cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b,
 
 }  // namespace
 
-cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int out_f32,
+cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int rp, int out_f32,
                             cudaStream_t stream) {
     const int gh = (H + p - 1) / p, gw = (W + p - 1) / p;
     const int pad_top = (gh * p - H) / 2, pad_left = (gw * p - W) / 2;
-    if (ldp < 3 * p * p) return cudaErrorInvalidValue;
-    dim3 grid(gh * p, B);
-    if (out_f32)
-        return launch_kernel(patchify_kernel<float>, grid, dim3(256), 0, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left,
-                             static_cast<float*>(patches), ldp);
-    return launch_kernel(patchify_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, 1, images, H, W, p, gh, gw, pad_top,
-                         pad_left, static_cast<__nv_bfloat16*>(patches), ldp);
+    if (rp < 3 * p || ldp < rp * p) return cudaErrorInvalidValue;
+    dim3 grid(gh, B);
+    const size_t smem = 0;
+    // vector stores need every run (and every token row) to start on a 4-element boundary
+    const bool vec = (rp % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
+    if (out_f32) {
+        float* o = static_cast<float*>(patches);
+        if (vec) return launch_kernel(patchify_kernel<float, true>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+        return launch_kernel(patchify_kernel<float, false>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+    }
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(patches);
+    if (vec) return launch_kernel(patchify_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+    return launch_kernel(patchify_kernel<__nv_bfloat16, false>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
 }
 
 cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D, float eps,
