@@ -270,6 +270,8 @@ struct vitdet_handle {
         std::vector<TcGemmPlan> qkv, out;
         std::vector<std::vector<TcGemmPlan>> mlp;
         std::vector<AttnPlan> attn;
+        bool tail_fused = false;              // last three MLP layers (+ residual + next LayerNorm) run as mlp_tail_kernel
+        std::vector<MlpTailPlan> tail;
     };
     std::map<int, EncPlans> enc_plans;      // key: images in the chunk
     struct HeadPlans {
@@ -495,6 +497,13 @@ static bool ln_is_fused(const vitdet_handle* h) {
     return v == 1 && h->D <= 32;
 }
 
+// VITDET_FUSE_TAIL=0 keeps the last three MLP layers as separate GEMM launches (A/B measurements).
+static bool tail_fusion_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VITDET_FUSE_TAIL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+    return v == 1;
+}
+
 static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
     GemmDesc g = make_desc(c, VITDET_MODE_BF16);
     int rc = make_tc_plan(plan, g, h->num_sms);
@@ -606,8 +615,33 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
         if (rc) return fail(VITDET_E_INVALID, "attn_bf16_make_plan failed: %d", rc);
         DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, xdummy, m.D4, xdummy, m.D4, 1, ACT_NONE, Mc};
         RC_TRY(plan_dense(h, with_ln(oc, b.ln2_g, b.ln2_b), &ep->out[i]));
+        // The last three layers fuse into one kernel when their widths fit it (default model: 224 -> 112 -> 56 -> 28).
+        bool tail = false;
+        if (fuse_ln && tail_fusion_enabled() && q >= 4) {
+            const int N3[3] = {b.mlp[q - 3].N, b.mlp[q - 2].N, b.mlp[q - 1].N};
+            const int K3[3] = {b.mlp[q - 3].K, b.mlp[q - 2].K, b.mlp[q - 1].K};
+            tail = mlp_tail_supported(N3, K3);
+        }
+        if (i == 0) { ep->tail_fused = tail; ep->tail.assign(tail ? L : 0, MlpTailPlan()); }
         const void* a = h->y.p; int lda = m.D8;
         for (int j = 0; j < q; ++j) {
+            if (tail && j == q - 3) {
+                MlpTailDesc td;
+                td.A = a; td.lda = lda; td.M = Mc;
+                for (int l = 0; l < 3; ++l) {
+                    DenseW& w = b.mlp[q - 3 + l];
+                    td.N[l] = w.N; td.K[l] = w.K; td.W[l] = w.w16.p; td.ldw[l] = w.ld16; td.bias[l] = w.bias.as<float>();
+                }
+                td.x = xdummy; td.ldx = m.D4; td.act = h->act;
+                if (i + 1 < L) {
+                    td.ln_gamma = h->blocks[i + 1].ln1_g.as<float>(); td.ln_beta = h->blocks[i + 1].ln1_b.as<float>();
+                    td.ln_eps = h->cfg.ln_epsilon; td.ln_out = h->y.p; td.ln_ld = m.D8;
+                }
+                int rc2 = mlp_tail_make_plan(&ep->tail[i], td, h->num_sms);
+                if (rc2) return fail(VITDET_E_INVALID, "mlp_tail_make_plan failed: %d", rc2);
+                ep->tail[i].valid = true;
+                break;
+            }
             const bool last = j == q - 1;
             void* o = last ? static_cast<void*>(xdummy) : ((j & 1) ? h->u1.p : h->u0.p);
             const int ldo = last ? m.D4 : round_up(b.mlp[j].N, 8);
@@ -775,6 +809,13 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
                 const bool last = j == q - 1;
                 void* o = last ? static_cast<void*>(x) : ((j & 1) ? h->u1.p : h->u0.p);
                 ProfScope ps(h, PC_MLP0 + j, st);
+                if (bf && ep->tail_fused && j == q - 3) {
+                    MlpTailPlan tp = ep->tail[i];       // by value: the residual-stream pointer is patched per chunk
+                    tp.desc.x = x;
+                    cudaError_t te = mlp_tail_launch(tp, st);
+                    if (te != cudaSuccess) return fail(VITDET_E_CUDA, "mlp_tail_launch failed: %s", cudaGetErrorString(te));
+                    break;
+                }
                 if (bf) {
                     RC_TRY(launch_tc(ep->mlp[i][j], o, last ? x : nullptr, st));
                 } else {

@@ -62,6 +62,34 @@ cudaError_t tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
 int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms);
 cudaError_t tc2_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------
+// Fused tail of the encoder MLP pyramid (mlp_tail.cu): x += act(W2 act(W1 act(W0 A + b0) + b1) + b2) in place on the
+// f32 residual stream x, optionally followed by LayerNorm -> bf16 (the next block's first LayerNorm).
+// ------------------------------------------------------------------------------------------------
+struct MlpTailDesc {
+    const void* A = nullptr; int lda = 0;      // bf16 [M, K[0]]
+    int M = 0;
+    int N[3] = {0, 0, 0}, K[3] = {0, 0, 0};
+    const void* W[3] = {nullptr, nullptr, nullptr}; int ldw[3] = {0, 0, 0};     // bf16 [N, K], K contiguous
+    const float* bias[3] = {nullptr, nullptr, nullptr};
+    float* x = nullptr; int ldx = 0;           // f32 [M, ldx]: residual in, result out
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 1e-3f;
+    void* ln_out = nullptr; int ln_ld = 0;     // bf16 [M, ln_ld] or null
+    int act = 0;
+};
+struct MlpTailPlan {
+    CUtensorMap tmA, tmW[3];
+    MlpTailDesc desc;
+    int npad[3], kb[3];
+    uint32_t off_w[3], off_act[2];
+    size_t smem_bytes = 0;
+    int num_tiles = 0, grid = 0;
+    bool valid = false;
+};
+bool mlp_tail_supported(const int N[3], const int K[3]);
+int mlp_tail_make_plan(MlpTailPlan* plan, const MlpTailDesc& d, int num_sms);
+cudaError_t mlp_tail_launch(const MlpTailPlan& plan, cudaStream_t stream);
+
 // f32 CUDA-core GEMM with the same epilogue (the fp32 parity mode); A, W, out are f32.
 // Requires lda, ldw multiples of 4 and zero padding of A and W in columns [K, round_up(K,4)).
 cudaError_t simt_gemm_launch(const GemmDesc& d, cudaStream_t stream);
