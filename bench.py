@@ -305,10 +305,15 @@ def run_ours(args):
         rows_total = B * cfg.tokens * args.steps * cfg.encoder_repeat_times     # rows pushed through this layer in the timed region
         flops_total = 2.0 * rows_total * K_ * N_
         achieved = flops_total / (ms_k * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel[{dominant}: K={K_} -> N={N_}, bias+Mish epilogue]",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_mlp_2_traffic.json")
+        if os.path.exists(tpath) and args.variant == "default" and B == 64:
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")      # from the committed ncu --set full capture
+        roofline = {"bound": "tensor", "kernel": f"{'gemm_tc2_kernel (CTA pair)' if K_ >= 512 and N_ >= 128 else 'gemm_tc_kernel'}[{dominant}: K={K_} -> N={N_}, bias+Mish epilogue]",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": peak_src, "launches": n_k, "avg_launch_ms": ms_k / n_k,
-                    "share_of_step": ms_k / (ms_step * args.steps), "traffic": None}
+                    "share_of_step": ms_k / (ms_step * args.steps), "traffic": traffic,
+                    "algorithmic_bytes": 2.0 * (B * cfg.tokens * (K_ + N_) + K_ * N_)}
 
     breakdown = None
     if args.breakdown:

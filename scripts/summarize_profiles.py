@@ -75,10 +75,34 @@ def full(tag, rep):
             f.write("\n")
 
 
+def traffic(tag):
+    """DRAM bytes per launch of the dominant GEMM (3584 -> 1792: the 2nd of the 3 captured gemm launches) for bench.py's
+    roofline.traffic field."""
+    import json
+    path = os.path.join(OUT, "prof_gemm.ncu-rep")
+    if not os.path.exists(path):
+        return
+    r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    rows = list(csv.reader(r.stdout.splitlines()))
+    if len(rows) < 4:
+        return
+    hdr, units, row = rows[0], rows[1], rows[3]
+    def val(name):
+        i = hdr.index(name)
+        v = float(row[i].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+    out = {"kernel": row[hdr.index("Kernel Name")][:80], "dram_bytes_read": val("dram__bytes_read.sum"),
+           "dram_bytes_write": val("dram__bytes_write.sum"), "source": f"profiles/{tag}_ncu_gemm.md (ncu --set full, B = 64)"}
+    out["traffic_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
+    with open(os.path.join(PROF, "gemm_mlp_2_traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
+    traffic(tag)
     for rep in sorted(x[:-8] for x in os.listdir(OUT) if x.endswith(".ncu-rep")):
         full(tag, rep)
     for name in ("bench_n1.json", "pytest_gpu.log"):

@@ -126,6 +126,29 @@ def test_default_model_bf16_logits():
     m.close()
 
 
+@pytest.mark.parametrize("name,cfg_kw", [
+    ("hires", dict(input_shape=(1024, 1024, 3), patch_size=16)),                                   # BASELINE configs[3]: 4096 tokens
+    ("vitb", dict(input_shape=(640, 640, 3), patch_size=16, embedding_dim=768, encoder_num_heads=12,
+                  encoder_key_dim=64, encoder_repeat_times=12, encoder_mlp_quantities=3)),          # BASELINE configs[4]
+])
+def test_variant_configs_bf16_match_the_float32_oracle(name, cfg_kw):
+    """The two variant configurations of BASELINE.json at their real shapes (one image).  The checker is the
+    float32 torch restatement (the float64 numpy one needs minutes at 4096 tokens); its own distance to
+    float64 is ~1e-6, far below the bf16 tolerance."""
+    cfg = vd.DetectorConfig(**cfg_kw)
+    w = vd.random_weights(cfg, seed=5, spread=True)
+    x = images(cfg, 1)
+    ref = oracle.forward_torch_f32(w, cfg, x)
+    m = build_model(cfg, w, "bf16")
+    got = m.predict(x)
+    assert got.shape == (1, 17, 6)
+    assert rel_err(got, ref) < TOL_BF16
+    rec = m.detect(x)                       # decode scales by the model's own input size
+    dref = oracle.decode(np.asarray(rec.logits, np.float64), image_size=cfg.input_shape[:2])
+    assert np.abs(rec.decoded - dref["decoded"]).max() < max(cfg.input_shape[:2]) * 2e-6
+    m.close()
+
+
 def test_device_tensor_path_equals_host_path():
     import torch
     cfg = tiny_config()
