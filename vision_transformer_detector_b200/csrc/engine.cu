@@ -1116,12 +1116,15 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     RC_TRY(h->dev_in.ensure(in_bytes));
     RC_TRY(h->dev_out.ensure(out_bytes));
     // Images are copied in sub-chunks of kGran images on a dedicated copy stream, one event per
-    // sub-chunk; the encoder runs chunks of 8, 16 and then `chunk` images, each waiting only for its own
-    // images: at ~12 images/ms of PCIe against ~4 images/ms of compute every copy but the first 8 images'
-    // (0.65 ms) hides behind the previous chunk's compute.  If the caller's
+    // sub-chunk; the encoder runs chunks of 4, 12 and then `chunk` images, each waiting only for its own
+    // images: at ~12 images/ms of PCIe against ~4 images/ms of compute every copy but the first 4 images'
+    // (0.33 ms) hides behind the previous chunk's compute (measured best of seven schedules, B = 64).  If the caller's
     // buffer is already page-locked the copy reads it directly; otherwise each sub-chunk is staged
     // through the handle's pinned buffer first (what a pageable cudaMemcpyAsync would do, serially).
-    constexpr int kGran = 8;
+    // VITDET_E2E_LEAD="g,a,b" overrides the copy granularity and the two lead chunk sizes (tuning experiments)
+    int kGran = 4, lead0 = 4, lead1 = 12;
+    if (const char* e = getenv("VITDET_E2E_LEAD")) sscanf(e, "%d,%d,%d", &kGran, &lead0, &lead1);
+    if (kGran < 1) kGran = 8;
     const int n_sub = (B + kGran - 1) / kGran;
     if (!h->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     while (static_cast<int>(h->copy_events.size()) < n_sub) {
@@ -1152,8 +1155,8 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
         CU_TRY(cudaEventRecord(h->copy_events[i], h->copy_stream));
     }
     ForwardOpts opts;
-    if (B > 3 * kGran) { opts.lead_chunks[0] = kGran; opts.lead_chunks[1] = 2 * kGran; }
-    else if (B > kGran) opts.lead_chunks[0] = kGran;
+    if (B > lead0 + lead1) { opts.lead_chunks[0] = lead0; opts.lead_chunks[1] = lead1; }
+    else if (B > lead0) opts.lead_chunks[0] = lead0;
     opts.ready = h->copy_events.data();
     opts.ready_gran = kGran;
     char* dbase = h->dev_out.as<char>();
