@@ -133,8 +133,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------ MMA issuer (leader CTA only) --------------
-        if (leader && lane == 0) {
+        // The WHOLE warp runs this loop (warp-uniform control flow keeps the loop state in uniform registers);
+        // only the tcgen05 instructions are issued by one elected lane.
+        if (leader) {
             const uint32_t idesc = umma_idesc_bf16_f32(2 * kBM, p.block_n);
+            const uint64_t da0 = umma_desc_sw128_kmajor(sA0), db0 = umma_desc_sw128_kmajor(sB0);
+            const uint32_t a_step = kStageBytesA >> 4, b_step = stage_bytes_b >> 4;      // descriptor address units (16 B)
+            const int last_steps = (p.K - (p.num_kb - 1) * kBK + kUK - 1) / kUK;         // k-steps of the last k-block (1..4)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -147,15 +152,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128_kmajor(sA0 + stage * kStageBytesA);
-                    const uint64_t db = umma_desc_sw128_kmajor(sB0 + stage * stage_bytes_b);
-                    int ksteps = kBK / kUK;
-                    if (kb == p.num_kb - 1) ksteps = (p.K - kb * kBK + kUK - 1) / kUK;
-                    for (int k = 0; k < ksteps; ++k) umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-                    umma_commit_2sm(bar_empty + 8 * stage, 3);          // frees the stage in both CTAs
+                    const int ksteps = (kb == p.num_kb - 1) ? last_steps : kBK / kUK;
+                    if (elect_one()) {
+                        const uint64_t da = da0 + static_cast<uint64_t>(stage * a_step), db = db0 + static_cast<uint64_t>(stage * b_step);
+                        umma_bf16_ss_2sm(d_tmem, da, db, idesc, kb != 0);
+                        if (ksteps > 1) umma_bf16_ss_2sm(d_tmem, da + 2u, db + 2u, idesc, 1u);
+                        if (ksteps > 2) umma_bf16_ss_2sm(d_tmem, da + 4u, db + 4u, idesc, 1u);
+                        if (ksteps > 3) umma_bf16_ss_2sm(d_tmem, da + 6u, db + 6u, idesc, 1u);
+                        umma_commit_2sm(bar_empty + 8 * stage, 3);          // frees the stage in both CTAs
+                        if (kb == p.num_kb - 1) umma_commit_2sm(bar_tfull + 8 * acc, 3);   // accumulators of both CTAs complete
+                    }
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit_2sm(bar_tfull + 8 * acc, 3);                // accumulators of both CTAs are complete
             }
         }
     } else {
