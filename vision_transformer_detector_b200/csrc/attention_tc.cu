@@ -214,39 +214,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0) {
-            const uint32_t idesc_qk = umma_idesc_bf16_f32(kQ, kKV);
-            const uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(kQ, kHP);
-            const uint32_t tP = tmem_base + kColP, tO = tmem_base + kColO;
-            const uint64_t dq = umma_desc_sw128_kmajor(sQ);
-            mbar_wait(bar_q, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j <= nkv; ++j) {
-                if (j < nkv) {
-                    // S = Q K(j)^T; the softmax warps moved S(j-1) into registers before signalling s_free
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    if (j >= 1) mbar_wait(bar_s_free, (j - 1) & 1);
-                    tc_fence_after();
-                    const uint64_t dk = umma_desc_sw128_kmajor(sKV + stage * 2 * kTileBytes);
-                    const uint32_t tS = tmem_base + kColS;
-                    for (int k = 0; k < p.k16; ++k) umma_bf16_ss(tS, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0);
+        // The whole warp runs the loop (warp-uniform control flow, loop state in uniform registers); only the
+        // tcgen05 instructions are issued by one elected lane.  Its wake-up-to-issue latency is on the critical
+        // path of every tile.
+        const uint32_t idesc_qk = umma_idesc_bf16_f32(kQ, kKV);
+        const uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(kQ, kHP);
+        const uint32_t tS = tmem_base + kColS, tP = tmem_base + kColP, tO = tmem_base + kColO;
+        const uint64_t dq = umma_desc_sw128_kmajor(sQ);
+        const uint64_t dkv0 = umma_desc_sw128_kmajor(sKV);
+        constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4, kVOff = kTileBytes >> 4;     // descriptor address units (16 B)
+        mbar_wait(bar_q, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j <= nkv; ++j) {
+            if (j < nkv) {
+                // S = Q K(j)^T; the softmax warps moved S(j-1) into registers before signalling s_free
+                mbar_wait(bar_full + 8 * stage, phase);
+                if (j >= 1) mbar_wait(bar_s_free, (j - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dk = dkv0 + static_cast<uint64_t>(stage * kStageStep);
+                    umma_bf16_ss(tS, dq, dk, idesc_qk, 0u);
+                    if (p.k16 > 1) umma_bf16_ss(tS, dq + 2u, dk + 2u, idesc_qk, 1u);
+                    if (p.k16 > 2) umma_bf16_ss(tS, dq + 4u, dk + 4u, idesc_qk, 1u);
+                    if (p.k16 > 3) umma_bf16_ss(tS, dq + 6u, dk + 6u, idesc_qk, 1u);
                     umma_commit(bar_s_full);
                 }
-                if (j > 0) {
-                    // O += P(j-1) V(j-1)
-                    const int ps = (j - 1) % kStages;
-                    mbar_wait(bar_p_full, (j - 1) & 1);
-                    tc_fence_after();
-                    const uint64_t dv = umma_desc_sw128_mnmajor(sKV + ps * 2 * kTileBytes + kTileBytes);
+                __syncwarp();
+            }
+            if (j > 0) {
+                // O += P(j-1) V(j-1)
+                const int ps = (j - 1) % kStages;
+                mbar_wait(bar_p_full, (j - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dv = dkv0 + static_cast<uint64_t>(ps * kStageStep + kVOff);
                     // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+#pragma unroll
                     for (int k = 0; k < kKV / 16; ++k)
-                        umma_bf16_ts(tO, tP + 8u * k, dv + static_cast<uint64_t>(128u * k), idesc_pv, (j > 1) || (k != 0));
+                        umma_bf16_ts(tO, tP + 8u * k, dv + static_cast<uint64_t>(128u * k), idesc_pv, (k != 0) ? 1u : (j > 1 ? 1u : 0u));
                     umma_commit(bar_empty + 8 * ps);
                     umma_commit(bar_pv_done);
                 }
-                if (j < nkv) { if (++stage == kStages) { stage = 0; phase ^= 1u; } }
+                __syncwarp();
             }
+            if (j < nkv) { if (++stage == kStages) { stage = 0; phase ^= 1u; } }
         }
     } else {
         // ------------------------------ softmax -----------------------------------

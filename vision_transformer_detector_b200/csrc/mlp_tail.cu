@@ -88,28 +88,32 @@ mlp_tail_kernel(const __grid_constant__ TailMaps maps, const TailArgs p) {
     pdl_wait();
 
     if (warp == kTailCtlWarp) {
-        if (lane == 0) {
-            // ---- weights, once ----
+        // The whole warp runs the control loop (warp-uniform); TMA / MMA / commit are issued by one elected lane.
+        const uint32_t a_bytes = static_cast<uint32_t>(p.kb[0]) * kATileBytes;
+        int tile = blockIdx.x;
+        if (elect_one()) {
+            // ---- weights, once; first A tile ----
             uint32_t wbytes = 0;
             for (int l = 0; l < 3; ++l) wbytes += static_cast<uint32_t>(p.kb[l] * p.npad[l] * 128);
             mbar_arrive_expect_tx(bar_w, wbytes);
             for (int l = 0; l < 3; ++l)
                 for (int kb = 0; kb < p.kb[l]; ++kb)
                     tma_load_2d(base + p.off_w[l] + kb * p.npad[l] * 128, &maps.w[l], bar_w, kb * kTK, 0);
-            const uint32_t a_bytes = static_cast<uint32_t>(p.kb[0]) * kATileBytes;
-            int tile = blockIdx.x;
             if (tile < p.num_tiles) {
                 mbar_arrive_expect_tx(bar_a, a_bytes);
                 for (int kb = 0; kb < p.kb[0]; ++kb) tma_load_2d(sA + kb * kATileBytes, &maps.a, bar_a, kb * kTK, tile * kTM);
             }
-            mbar_wait(bar_w, 0);
-            uint32_t ph = 0;
-            for (; tile < p.num_tiles; tile += gridDim.x, ph ^= 1u) {
-                for (int l = 0; l < 3; ++l) {
-                    uint32_t a_base;
-                    if (l == 0) { mbar_wait(bar_a, ph); a_base = sA; }
-                    else { mbar_wait(bar_act + 8 * (l - 1), ph); a_base = base + p.off_act[l - 1]; }
-                    tc_fence_after();
+        }
+        __syncwarp();
+        mbar_wait(bar_w, 0);
+        uint32_t ph = 0;
+        for (; tile < p.num_tiles; tile += gridDim.x, ph ^= 1u) {
+            for (int l = 0; l < 3; ++l) {
+                uint32_t a_base;
+                if (l == 0) { mbar_wait(bar_a, ph); a_base = sA; }
+                else { mbar_wait(bar_act + 8 * (l - 1), ph); a_base = base + p.off_act[l - 1]; }
+                tc_fence_after();
+                if (elect_one()) {
                     if (l == 1) {
                         // MMA 0 is complete (its epilogue has run): the A buffer is free for the next tile
                         const int nt = tile + gridDim.x;
@@ -129,6 +133,7 @@ mlp_tail_kernel(const __grid_constant__ TailMaps maps, const TailArgs p) {
                     }
                     umma_commit(bar_d + 8 * l);
                 }
+                __syncwarp();
             }
         }
     } else {
