@@ -62,17 +62,9 @@ static int fail(int code, const char* fmt, ...) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// VITDET_ATTN=legacy selects the mma.sync attention kernel, for A/B measurements only.
-static bool use_legacy_attention() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VITDET_ATTN"); v = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
-    return v == 1;
-}
-static cudaError_t attn_launch(const AttnPlan& plan, cudaStream_t st) {
-    return use_legacy_attention() ? attn_bf16_launch(plan, st) : attn_tc_launch(plan, st);
-}
-
 constexpr int kHeadPitch = 64;   // elements per head slot in qkv / ctx (one 128-byte swizzle row of bf16)
+
+static cudaError_t attn_launch(const AttnPlan& plan, cudaStream_t st) { return attn_tc_launch(plan, st); }
 
 // ------------------------------------------------------------------------------------------------
 // weight packing kernels (run once per set_weight)

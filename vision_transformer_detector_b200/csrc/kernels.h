@@ -111,7 +111,6 @@ struct AttnPlan {
     AttnDesc desc;
 };
 int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d);
-cudaError_t attn_bf16_launch(const AttnPlan& plan, cudaStream_t stream);   // legacy mma.sync kernel (A/B measurements only)
 cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tcgen05 kernel (attention_tc.cu)
 cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 
