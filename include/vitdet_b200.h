@@ -158,6 +158,13 @@ int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* pa
 int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_params* params,
                        const vitdet_detections* out_host);
 
+/* Replaces iou_calculator(label_bbox, prediction_bbox) (det.py:761-875; "next" row N2 of the hot-path table):
+ * element-wise IoU of R box pairs.  Each box is the LAST FOUR floats (cx, cy, h, w — actual pixels) of a row of
+ * `width` floats (4 for plain boxes, 6 for label / decoded-prediction rows); iou[r] = I / (U + Constants.EPSILON).
+ * vitdet_iou takes DEVICE pointers and is asynchronous; vitdet_iou_host takes HOST pointers and synchronises. */
+int vitdet_iou(const float* label_dev, const float* pred_dev, int64_t R, int width, float* iou_dev, void* stream);
+int vitdet_iou_host(const float* label_host, const float* pred_host, int64_t R, int width, float* iou_host);
+
 /* Forward with the decode fused into the head's last Dense (one launch fewer, logits never re-read).
  * logits_dev may be NULL. */
 int vitdet_forward_decode(vitdet_handle* h, const float* images_dev, int B, int mode,

@@ -251,6 +251,30 @@ def decode(logits: np.ndarray, image_size=MODEL_IMAGE_SIZE, objectness_threshold
     return {"decoded": dec, "class_id": cid, "class_conf": cc, "keep": keep, "corners": corners(dec, image_size)}
 
 
+EPSILON = 1e-8                     # Constants.EPSILON det.py:24
+
+
+def iou_calculator(label_bbox: np.ndarray, prediction_bbox: np.ndarray) -> np.ndarray:
+    """det.py:761-875, statement by statement: edges, strict overlap test, zero the edges of non-overlapping pairs,
+    sort the four edges, intersection = sorted[-2] - sorted[-3] per axis, IoU = I / (U + EPSILON).  Boxes are the last
+    four entries (center_x, center_y, height, width) of the last axis.  Pinned by the reference's own known answers
+    (tests.py:170-195: 0.64; tests.py:223-248: 0.49)."""
+    lb, pb = np.asarray(label_bbox), np.asarray(prediction_bbox)
+    half = lb.dtype.type(2)
+    l_left, l_right = lb[..., -4] - lb[..., -1] / half, lb[..., -4] + lb[..., -1] / half            # det.py:789-790
+    p_left, p_right = pb[..., -4] - pb[..., -1] / half, pb[..., -4] + pb[..., -1] / half            # det.py:791-794
+    l_top, l_bottom = lb[..., -3] - lb[..., -2] / half, lb[..., -3] + lb[..., -2] / half            # det.py:796-797
+    p_top, p_bottom = pb[..., -3] - pb[..., -2] / half, pb[..., -3] + pb[..., -2] / half            # det.py:798-801
+    hit = (l_left < p_right) & (l_right > p_left) & (l_top < p_bottom) & (l_bottom > p_top)         # det.py:806-817
+    hor = np.stack([l_top, l_bottom, p_top, p_bottom], axis=-1)                                     # det.py:826-828
+    ver = np.stack([l_left, l_right, p_left, p_right], axis=-1)
+    hor = np.sort(np.where(hit[..., None], hor, 0), axis=-1)                                        # det.py:837-845
+    ver = np.sort(np.where(hit[..., None], ver, 0), axis=-1)
+    inter = (hor[..., -2] - hor[..., -3]) * (ver[..., -2] - ver[..., -3])                           # det.py:849-853
+    union = pb[..., -1] * pb[..., -2] + lb[..., -1] * lb[..., -2] - inter                           # det.py:856-866
+    return inter / (union + lb.dtype.type(EPSILON))                                                 # det.py:873
+
+
 # ------------------------------------------------------------------------------------------------
 # torch float32 restatement on the host cores (the timed CPU baseline: "TF on CPU" stand-in)
 # ------------------------------------------------------------------------------------------------

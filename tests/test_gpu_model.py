@@ -201,3 +201,28 @@ def test_transform_predictions_and_corners_match_oracle():
         assert np.array_equal(rec.corners[fin], oracle.corners(rec.decoded.astype(np.float32), size)[fin])
     e = vd.decode_predictions(np.zeros((0, 17, 6), np.float32))
     assert e.decoded.shape == (0, 17, 6) and e.keep.shape == (0, 17)
+
+
+def test_iou_calculator_is_bit_exact_and_reproduces_known_answers():
+    """N2 (first part): the reference's iou_calculator on the GPU, against its own test values and bit-exactly
+    against the float32 oracle on random boxes (overlapping, disjoint, touching, degenerate)."""
+    import torch
+    g = json.load(open(GOLDEN))
+    for row in g["iou"]:
+        a = np.array([[[0.0, 79.0, *row["a"]]]], np.float32)
+        b = np.array([[[0.0, 79.0, *row["b"]]]], np.float32)
+        assert abs(float(vd.iou_calculator(a, b)[0, 0]) - row["iou"]) < 1e-6
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 608, size=(64, 17, 6)).astype(np.float32)
+    b = a + rng.normal(0, 40, size=a.shape).astype(np.float32)
+    b[..., 4:] = np.abs(b[..., 4:])
+    b[0] = a[0]                                  # identical boxes
+    b[1, :, 2] = a[1, :, 2] + a[1, :, 5]         # touching / shifted by a full width
+    a[2, :, 4:] = 0                              # zero-area labels
+    ref = oracle.iou_calculator(a, b)
+    got = vd.iou_calculator(a, b)
+    assert got.shape == (64, 17) and got.dtype == np.float32
+    assert np.array_equal(got, ref)
+    dev = vd.iou_calculator(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert np.array_equal(dev.cpu().numpy(), ref)
+    assert vd.iou_calculator(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32)).shape == (0,)

@@ -124,3 +124,18 @@ def test_attention_core_equals_mha_without_projections():
     v = np.einsum("abc,cde->abde", x, wv) + bv
     o = oracle.attention_core(q, k, v)
     assert np.allclose(np.einsum("abcd,cde->abe", o, wo) + bo, full, atol=1e-12)
+
+
+def test_iou_calculator_matches_reference_known_answers():
+    """tests.py:170-195 (IoU 0.64 -> AP 0.3) and tests.py:223-248 (IoU 0.49 -> AP 0)."""
+    g = json.load(open(GOLDEN))
+    for row in g["iou"]:
+        a = np.array([[1.0, 79.0, *row["a"]]], np.float32)
+        b = np.array([[1.0, 79.0, *row["b"]]], np.float32)
+        assert abs(float(oracle.iou_calculator(a, b)[0]) - row["iou"]) < 1e-6
+    same = np.array([[3.0, 4.0, 5.0, 6.0]], np.float64)
+    assert abs(oracle.iou_calculator(same, same)[0] - 1.0) < 1e-9
+    apart = np.array([[100.0, 100.0, 5.0, 6.0]], np.float64)
+    assert oracle.iou_calculator(same, apart)[0] == 0.0
+    touching = np.array([[9.0, 4.0, 5.0, 6.0]], np.float64)      # shares an edge: strict comparison -> no overlap
+    assert oracle.iou_calculator(same, touching)[0] == 0.0

@@ -8,6 +8,7 @@ from .vision_transformer_detector import (  # noqa: F401
     VisionTransformerDetector,
     create_vision_transformer_detector,
     decode_predictions,
+    iou_calculator,
     mlp_head,
     random_weights,
     transform_predictions,
@@ -18,6 +19,6 @@ from .vision_transformer_detector import (  # noqa: F401
 
 __all__ = [
     "Constants", "DetectionRecords", "DetectorConfig", "VisionTransformerDetector",
-    "create_vision_transformer_detector", "decode_predictions", "mlp_head", "random_weights",
+    "create_vision_transformer_detector", "decode_predictions", "iou_calculator", "mlp_head", "random_weights",
     "transform_predictions", "transformer_encoder", "transformer_preprocessor", "weight_specs",
 ]

@@ -82,6 +82,8 @@ SYMBOLS = {
     "vitdet_forward": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "vitdet_decode": (C.c_int, [_P, C.c_int, C.POINTER(DecodeParams), C.POINTER(Detections), _P]),
     "vitdet_decode_host": (C.c_int, [_P, C.c_int, C.POINTER(DecodeParams), C.POINTER(Detections)]),
+    "vitdet_iou": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
+    "vitdet_iou_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "vitdet_forward_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),
     "vitdet_predict_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),
     "vitdet_op_dense": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

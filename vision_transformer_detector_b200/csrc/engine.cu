@@ -1058,6 +1058,25 @@ int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* p,
     return 0;
 }
 
+int vitdet_iou(const float* label_dev, const float* pred_dev, int64_t R, int width, float* iou_dev, void* stream) {
+    if (!label_dev || !pred_dev || !iou_dev || R < 0 || width < 4) return fail(VITDET_E_INVALID, "iou: bad arguments");
+    CU_TRY(iou_launch(label_dev, pred_dev, R, width, 1e-8f /* Constants.EPSILON, det.py:24 */, iou_dev, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int vitdet_iou_host(const float* label_host, const float* pred_host, int64_t R, int width, float* iou_host) {
+    if (!label_host || !pred_host || !iou_host || R < 0 || width < 4) return fail(VITDET_E_INVALID, "iou_host: bad arguments");
+    if (R == 0) return 0;
+    const size_t nb = static_cast<size_t>(R) * width * 4;
+    DevBuf a, b, o;
+    RC_TRY(a.ensure(nb)); RC_TRY(b.ensure(nb)); RC_TRY(o.ensure(static_cast<size_t>(R) * 4));
+    CU_TRY(cudaMemcpy(a.p, label_host, nb, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b.p, pred_host, nb, cudaMemcpyHostToDevice));
+    RC_TRY(vitdet_iou(a.as<float>(), b.as<float>(), R, width, o.as<float>(), nullptr));
+    CU_TRY(cudaMemcpy(iou_host, o.p, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_params* p, const vitdet_detections* out_host) {
     if (!logits_host || !p || !out_host || R < 0) return fail(VITDET_E_INVALID, "decode_host: bad arguments");
     if (R == 0) return 0;

@@ -153,5 +153,8 @@ cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w 
                              int R, int U, const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream);
 cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,
                           cudaStream_t stream);
+// iou_calculator (det.py:761-875): element-wise IoU of (cx, cy, h, w) boxes in the last four entries of `width`-wide rows.
+cudaError_t iou_launch(const float* label, const float* pred, long long R, int width, float eps, float* iou,
+                       cudaStream_t stream);
 
 }  // namespace vitdet

@@ -311,6 +311,41 @@ decode_kernel(const float* __restrict__ logits, int R, DecodeParams dp, DecodeOu
     decode_slot(l, r, dp, o2);
 }
 
+// ------------------------------------------------------------------------------------------------
+// iou_calculator (reference det.py:761-875): element-wise IoU of boxes (cx, cy, h, w) held in the LAST FOUR
+// entries of rows of `width` floats.  Same arithmetic and operation order as the reference (edges, strict '<' / '>'
+// overlap test, the two middle values of the four sorted edges, I / (U + eps)); __f*_rn intrinsics keep the
+// compiler from contracting products and sums into FMAs, so the result is bit-identical to an f32 evaluation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sort2(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+
+__device__ __forceinline__ float middle_extent(float a, float b, float c, float d) {
+    sort2(a, b); sort2(c, d); sort2(a, c); sort2(b, d); sort2(b, c);      // a <= b <= c <= d
+    return __fsub_rn(c, b);                                                // sorted[-2] - sorted[-3]
+}
+
+__global__ void __launch_bounds__(256)
+iou_kernel(const float* __restrict__ label, const float* __restrict__ pred, long long R, int width, float eps,
+           float* __restrict__ iou) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* lb = label + r * width + (width - 4);
+    const float* pb = pred + r * width + (width - 4);
+    const float lx = lb[0], ly = lb[1], lh = lb[2], lw = lb[3];
+    const float px = pb[0], py = pb[1], ph = pb[2], pw = pb[3];
+    const float l_left = __fsub_rn(lx, __fmul_rn(lw, 0.5f)), l_right = __fadd_rn(lx, __fmul_rn(lw, 0.5f));
+    const float p_left = __fsub_rn(px, __fmul_rn(pw, 0.5f)), p_right = __fadd_rn(px, __fmul_rn(pw, 0.5f));
+    const float l_top = __fsub_rn(ly, __fmul_rn(lh, 0.5f)), l_bottom = __fadd_rn(ly, __fmul_rn(lh, 0.5f));
+    const float p_top = __fsub_rn(py, __fmul_rn(ph, 0.5f)), p_bottom = __fadd_rn(py, __fmul_rn(ph, 0.5f));
+    const bool hit = (l_left < p_right) && (l_right > p_left) && (l_top < p_bottom) && (l_bottom > p_top);
+    float inter = 0.f;
+    if (hit) inter = __fmul_rn(middle_extent(l_top, l_bottom, p_top, p_bottom), middle_extent(l_left, l_right, p_left, p_right));
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(pw, ph), __fmul_rn(lw, lh)), inter);
+    iou[r] = __fdiv_rn(inter, __fadd_rn(uni, eps));
+}
+
 template <int LPR, typename T>
 cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b, int M, int D, float eps, T* y,
                         int ldy, cudaStream_t st) {
@@ -378,6 +413,13 @@ cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w,
                              bias, R, U, dp, out);
     return launch_kernel(head_tail_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1,
                          static_cast<const __nv_bfloat16*>(h), ldh, w, bias, R, U, dp, out);
+}
+
+cudaError_t iou_launch(const float* label, const float* pred, long long R, int width, float eps, float* iou,
+                       cudaStream_t stream) {
+    if (R <= 0) return cudaSuccess;
+    if (width < 4) return cudaErrorInvalidValue;
+    return launch_kernel(iou_kernel, dim3(static_cast<unsigned>((R + 255) / 256)), dim3(256), 0, stream, 1, label, pred, R, width, eps, iou);
 }
 
 cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,

@@ -327,6 +327,31 @@ def transform_predictions(inputs, image_size=None):
     return decode_predictions(inputs, image_size=image_size).decoded
 
 
+def iou_calculator(label_bbox, prediction_bbox):
+    """det.py:761-875: element-wise IoU of two equally shaped box arrays whose last axis ends with
+    (center_x, center_y, height, width) in pixels; returns the array without its last axis.  numpy in ->
+    numpy out, torch CUDA tensors in -> torch CUDA tensor out (computed on the GPU either way)."""
+    lib = _capi.load()
+    if _is_torch_cuda(label_bbox) or _is_torch_cuda(prediction_bbox):
+        import torch
+        a = label_bbox.to(torch.float32).contiguous()
+        b = prediction_bbox.to(device=a.device, dtype=torch.float32).contiguous()
+        if a.shape != b.shape or a.shape[-1] < 4:
+            raise ValueError(f"label_bbox {tuple(a.shape)} and prediction_bbox {tuple(b.shape)} must have the same shape (..., >= 4)")
+        out = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _capi.check(lib.vitdet_iou(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), out.numel(), int(a.shape[-1]),
+                                       C.c_void_p(out.data_ptr()), _torch_stream_ptr(a.device)))
+        return out
+    a = np.ascontiguousarray(np.asarray(label_bbox, dtype=np.float32))
+    b = np.ascontiguousarray(np.asarray(prediction_bbox, dtype=np.float32))
+    if a.shape != b.shape or a.shape[-1] < 4:
+        raise ValueError(f"label_bbox {a.shape} and prediction_bbox {b.shape} must have the same shape (..., >= 4)")
+    out = np.empty(a.shape[:-1], np.float32)
+    _capi.check(lib.vitdet_iou_host(_capi.np_ptr(a), _capi.np_ptr(b), out.size, int(a.shape[-1]), _capi.np_ptr(out)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the model object
 # ------------------------------------------------------------------------------------------------
