@@ -131,6 +131,8 @@ typedef struct vitdet_decode_params {
     int32_t use_transform_predictions; /* 1 (default): inputs are raw logits, apply transform_predictions first;
                                           0: inputs are already decoded rows (the `use_transform_predictions=False`
                                           path of MeanAveragePrecision.update_state, det.py:1340-1341) */
+    float corner_scale;                /* enlarged_image_scale of visualize_predictions (det.py:2294-2325): the corner boxes are
+                                          int(cx*s -/+ w*s/2), int(cy*s -/+ h*s/2) clipped to the enlarged image; 0 or 1 = no scaling */
 } vitdet_decode_params;
 
 /* Output record arrays of the decode, all DEVICE pointers, any of them may be NULL:

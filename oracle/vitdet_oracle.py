@@ -232,11 +232,13 @@ def threshold(decoded: np.ndarray, objectness_threshold: float = OBJECTNESS_THRE
     return cid.astype(np.int32), cc, keep
 
 
-def corners(decoded: np.ndarray, image_size=MODEL_IMAGE_SIZE) -> np.ndarray:
-    """det.py:2294-2325 with enlarged_image_scale = 1: int() truncation, then clip to the image."""
+def corners(decoded: np.ndarray, image_size=MODEL_IMAGE_SIZE, scale: float = 1.0) -> np.ndarray:
+    """det.py:2294-2325: boxes times enlarged_image_scale, int() truncation, then clip to the (enlarged) image, whose
+    size is round(size * scale) (det.py:2237-2252)."""
     dec = np.asarray(decoded)
-    ih, iw = image_size
-    cx, cy, bh, bw = dec[..., 2], dec[..., 3], dec[..., 4], dec[..., 5]
+    s = dec.dtype.type(scale)
+    ih, iw = (int(round(float(dec.dtype.type(v) * s))) for v in image_size)
+    cx, cy, bh, bw = dec[..., 2] * s, dec[..., 3] * s, dec[..., 4] * s, dec[..., 5] * s
     x0 = np.clip(np.trunc(cx - bw / 2).astype(np.int64), 0, int(iw))
     y0 = np.clip(np.trunc(cy - bh / 2).astype(np.int64), 0, int(ih))
     x1 = np.clip(np.trunc(cx + bw / 2).astype(np.int64), 0, int(iw))

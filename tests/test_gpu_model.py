@@ -226,3 +226,39 @@ def test_iou_calculator_is_bit_exact_and_reproduces_known_answers():
     dev = vd.iou_calculator(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
     assert np.array_equal(dev.cpu().numpy(), ref)
     assert vd.iou_calculator(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32)).shape == (0,)
+
+
+def _logit(p):
+    return float(np.log(p / (1 - p)))
+
+
+def test_visualize_predictions_draws_the_kept_slots():
+    """N3: thresholds, class ids and corner boxes come from the device decode (visualise rule); the host only draws."""
+    B, H, W = 2, 608, 608
+    imgs = np.zeros((B, H, W, 3), np.float32) - 1.0                  # black images
+    logits = np.full((B, 17, 6), -20.0, np.float32)                  # every slot rejected ...
+    # ... except: image 0 slot 3 = class 16 ("dog") at (cx 300.4, cy 200.4, h 100, w 60); image 1 slot 0 exactly AT the objectness threshold
+    # (centres end in .4 so that float rounding cannot move an int() truncation across an integer)
+    logits[0, 3] = [_logit(0.9), _logit(16.1 / 79), _logit(300.4 / 608), _logit(200.4 / 608), _logit(100 / 608), _logit(60 / 608)]
+    logits[1, 0] = [0.0, _logit(2.0 / 79), _logit(100.4 / 608), _logit(100.4 / 608), _logit(40 / 608), _logit(40 / 608)]
+    out = vd.visualize_predictions(imgs, predictions=logits)
+    assert len(out) == 2 and out[0].shape == (H, W, 3) and out[0].dtype == np.uint8
+    green = lambda im: (im[..., 1] == 255) & (im[..., 0] == 0) & (im[..., 2] == 0)
+    g0 = green(out[0])
+    assert g0[150, 270:330].all() and g0[250, 270:330].all() and g0[150:250, 270].all() and g0[150:250, 330].all()   # the rectangle
+    assert not g0[200, 300]                                                                                         # hollow
+    assert green(out[1])[80, 80:120].all()                 # objectness == 0.5 is kept by the visualise rule (skip only if '<')
+    rec = vd.decode_predictions(logits, strict=False)
+    assert rec.keep.sum() == 2 and rec.class_id[0, 3] == 16 and tuple(rec.corners[0, 3]) == (270, 150, 330, 250)
+    assert vd.decode_predictions(logits, strict=True).keep.sum() == 1      # the metric rule drops the slot at the threshold
+    # enlarged_image_scale: boxes and clip bounds scale, int() truncation after scaling
+    big = vd.visualize_predictions(imgs[:1], predictions=logits[:1], enlarged_image_scale=1.5)
+    assert big[0].shape == (912, 912, 3) and green(big[0])[225, 405:495].all()
+    for scale in (1.0, 1.5, 0.7):
+        r = vd.decode_predictions(logits, strict=False, corner_scale=scale)
+        assert np.array_equal(r.corners, oracle.corners(r.decoded.astype(np.float32), (608, 608), scale))
+    # label batches (already decoded rows, no confidence text): det.py:2420-2436
+    labels = np.full((1, 17, 6), -8.0, np.float32); labels[..., 0] = 0
+    labels[0, 1] = [1, 79, 10.2, 10.2, 10, 10]
+    lab = vd.visualize_predictions([(imgs[:1], labels)])
+    assert len(lab) == 1 and green(lab[0])[5, 5:15].all()

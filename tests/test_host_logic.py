@@ -67,7 +67,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_capi.Config) == 15 * 4
-    assert ctypes.sizeof(_capi.DecodeParams) == 7 * 4
+    assert ctypes.sizeof(_capi.DecodeParams) == 8 * 4
     assert ctypes.sizeof(_capi.Detections) == 5 * ctypes.sizeof(ctypes.c_void_p)
     c = _capi.default_config()
     assert (c.image_h, c.image_w, c.patch_size, c.embedding_dim, c.num_heads, c.key_dim) == (608, 608, 17, 28, 8, 40)
@@ -94,3 +94,14 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "vitdet_oracle" not in text and "import oracle" not in text, f"{f} references the oracle"
+
+
+def test_category_names_match_the_reference_table():
+    """full_categories.csv of the reference (id_in_model -> name); only checkable where the reference is mounted."""
+    path = "/root/reference/full_categories.csv"
+    assert len(vd.COCO_CATEGORY_NAMES) == 80 and vd.COCO_CATEGORY_NAMES[0] == "person" and vd.COCO_CATEGORY_NAMES[79] == "toothbrush"
+    if not os.path.exists(path):
+        pytest.skip("reference not mounted")
+    import csv
+    rows = list(csv.DictReader(open(path)))
+    assert [r["name"] for r in sorted(rows, key=lambda r: float(r["id_in_model"]))] == list(vd.COCO_CATEGORY_NAMES)

@@ -17,7 +17,10 @@ from .vision_transformer_detector import (  # noqa: F401
     weight_specs,
 )
 
+from .visualization import COCO_CATEGORY_NAMES, visualize_predictions  # noqa: F401,E402
+
 __all__ = [
+    "COCO_CATEGORY_NAMES", "visualize_predictions",
     "Constants", "DetectionRecords", "DetectorConfig", "VisionTransformerDetector",
     "create_vision_transformer_detector", "decode_predictions", "iou_calculator", "mlp_head", "random_weights",
     "transform_predictions", "transformer_encoder", "transformer_preprocessor", "weight_specs",

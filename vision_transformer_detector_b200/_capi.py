@@ -46,6 +46,7 @@ class DecodeParams(C.Structure):
         ("image_h", C.c_float), ("image_w", C.c_float),
         ("classes", C.c_int32),
         ("use_transform_predictions", C.c_int32),
+        ("corner_scale", C.c_float),
     ]
 
 

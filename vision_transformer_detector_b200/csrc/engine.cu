@@ -852,6 +852,7 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
         dp.obj_thr = dpar->objectness_threshold; dp.cls_thr = dpar->classification_threshold;
         dp.strict = dpar->strict; dp.img_h = dpar->image_h; dp.img_w = dpar->image_w; dp.classes = dpar->classes;
         dp.apply_transform = 1;   // the head emits raw logits
+        dp.corner_scale = dpar->corner_scale > 0.f ? dpar->corner_scale : 1.f;
     }
     if (det) {
         dout.decoded = det->decoded; dout.class_id = det->class_id; dout.class_conf = det->class_conf;
@@ -1052,6 +1053,7 @@ int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* p,
     dp.obj_thr = p->objectness_threshold; dp.cls_thr = p->classification_threshold; dp.strict = p->strict;
     dp.img_h = p->image_h; dp.img_w = p->image_w; dp.classes = p->classes;
     dp.apply_transform = p->use_transform_predictions ? 1 : 0;
+    dp.corner_scale = p->corner_scale > 0.f ? p->corner_scale : 1.f;
     DecodeOut o;
     o.decoded = out->decoded; o.class_id = out->class_id; o.class_conf = out->class_conf; o.keep = out->keep; o.corners = out->corners;
     CU_TRY(decode_launch(logits_dev, R, dp, o, static_cast<cudaStream_t>(stream)));

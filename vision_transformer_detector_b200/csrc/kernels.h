@@ -140,6 +140,7 @@ struct DecodeParams {
     float img_h = 608.f, img_w = 608.f;
     int classes = 80;
     int apply_transform = 1;    // 0: rows are already transform_predictions output (det.py:1340-1341)
+    float corner_scale = 1.f;   // enlarged_image_scale (det.py:2294-2297)
 };
 struct DecodeOut {
     float* logits = nullptr;    // [R, 6] raw (optional when decoding given logits)

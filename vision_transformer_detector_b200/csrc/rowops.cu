@@ -256,11 +256,15 @@ __device__ __forceinline__ void decode_slot(const float (&l)[6], long long r, co
     if (o.keep) o.keep[r] = keep ? 1 : 0;
     if (o.corners) {
         // det.py:2300-2325: int() truncation toward zero, then clip to the image.
-        const int iw = static_cast<int>(dp.img_w), ih = static_cast<int>(dp.img_h);
-        o.corners[r * 4 + 0] = clip_int(static_cast<int>(dec[2] - dec[5] / 2.f), 0, iw);
-        o.corners[r * 4 + 1] = clip_int(static_cast<int>(dec[3] - dec[4] / 2.f), 0, ih);
-        o.corners[r * 4 + 2] = clip_int(static_cast<int>(dec[2] + dec[5] / 2.f), 0, iw);
-        o.corners[r * 4 + 3] = clip_int(static_cast<int>(dec[3] + dec[4] / 2.f), 0, ih);
+        // boxes are scaled by enlarged_image_scale first (det.py:2294-2297); the clip bounds are the enlarged image's
+        // width / height, round(size * scale) (det.py:2237-2252)
+        const float s = dp.corner_scale;
+        const int iw = static_cast<int>(rintf(dp.img_w * s)), ih = static_cast<int>(rintf(dp.img_h * s));
+        const float cx = dec[2] * s, cy = dec[3] * s, bh = dec[4] * s, bw = dec[5] * s;
+        o.corners[r * 4 + 0] = clip_int(static_cast<int>(cx - bw / 2.f), 0, iw);
+        o.corners[r * 4 + 1] = clip_int(static_cast<int>(cy - bh / 2.f), 0, ih);
+        o.corners[r * 4 + 2] = clip_int(static_cast<int>(cx + bw / 2.f), 0, iw);
+        o.corners[r * 4 + 3] = clip_int(static_cast<int>(cy + bh / 2.f), 0, ih);
     }
 }
 

@@ -241,7 +241,7 @@ class DetectionRecords:
 
 
 def _decode_params(objectness_threshold, classification_threshold, strict, image_size,
-                   use_transform_predictions=True) -> _capi.DecodeParams:
+                   use_transform_predictions=True, corner_scale=1.0) -> _capi.DecodeParams:
     p = _capi.DecodeParams()
     p.objectness_threshold = Constants.OBJECTNESS_THRESHOLD.value if objectness_threshold is None else float(objectness_threshold)
     p.classification_threshold = (Constants.CLASSIFICATION_CONFIDENCE_THRESHOLD.value
@@ -251,6 +251,7 @@ def _decode_params(objectness_threshold, classification_threshold, strict, image
     p.image_h, p.image_w = float(ih), float(iw)
     p.classes = Constants.CLASSES.value
     p.use_transform_predictions = 1 if use_transform_predictions else 0
+    p.corner_scale = float(corner_scale)
     return p
 
 
@@ -286,7 +287,7 @@ def _records_struct(decoded, class_id, class_conf, keep, corners) -> _capi.Detec
 
 
 def decode_predictions(predictions, objectness_threshold=None, classification_threshold=None, strict=True,
-                       image_size=None, use_transform_predictions=True) -> DetectionRecords:
+                       image_size=None, use_transform_predictions=True, corner_scale=1.0) -> DetectionRecords:
     """transform_predictions + the score thresholds + class ids + corner boxes, on the GPU.
 
     predictions: raw logits (..., 17, 6) — numpy (host) or torch CUDA tensor.
@@ -297,7 +298,7 @@ def decode_predictions(predictions, objectness_threshold=None, classification_th
     (the flag of MeanAveragePrecision.update_state, det.py:1340-1341)."""
     lib = _capi.load()
     params = _decode_params(objectness_threshold, classification_threshold, strict, image_size,
-                            use_transform_predictions)
+                            use_transform_predictions, corner_scale)
     if _is_torch_cuda(predictions):
         import torch
         x = predictions.to(torch.float32).contiguous()
