@@ -167,6 +167,15 @@ int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_para
 int vitdet_iou(const float* label_dev, const float* pred_dev, int64_t R, int width, float* iou_dev, void* stream);
 int vitdet_iou_host(const float* label_host, const float* pred_host, int64_t R, int width, float* iou_host);
 
+/* Input side ("next" row N4): what _get_image_tensor_coco (vision_transformer_utilities.py:418-449) does after decoding
+ * the file: tf.image.resize_with_pad(image, target_h, target_w) (bilinear, half-pixel centres, zero padding), clip to
+ * [0, 255], / 127.5, - 1.  image: uint8 [h, w, 3]; out: float32 [target_h, target_w, 3] in [-1, 1].
+ * vitdet_preprocess_image takes DEVICE pointers and is asynchronous; the _host variant takes HOST pointers. */
+int vitdet_preprocess_image(const uint8_t* image_dev, int h, int w, float* out_dev, int target_h, int target_w, void* stream);
+int vitdet_preprocess_image_host(const uint8_t* image_host, int h, int w, float* out_host, int target_h, int target_w);
+/* The geometry resize_with_pad derives (resized height / width, top / left padding), in TF's float32 arithmetic. */
+int vitdet_resize_with_pad_geometry(int h, int w, int target_h, int target_w, int* resized_h, int* resized_w, int* pad_top, int* pad_left);
+
 /* Forward with the decode fused into the head's last Dense (one launch fewer, logits never re-read).
  * logits_dev may be NULL. */
 int vitdet_forward_decode(vitdet_handle* h, const float* images_dev, int B, int mode,

@@ -253,6 +253,47 @@ def decode(logits: np.ndarray, image_size=MODEL_IMAGE_SIZE, objectness_threshold
     return {"decoded": dec, "class_id": cid, "class_conf": cc, "keep": keep, "corners": corners(dec, image_size)}
 
 
+def resize_with_pad_geometry(h: int, w: int, th: int, tw: int):
+    """Size arithmetic of tf.image.resize_with_pad (TF 2.9 image_ops_impl._resize_with_pad_common), in float32 as TF
+    computes it: ratio = max(w/tw, h/th); resized = floor(size / ratio); pad = max(0, floor((target - size/ratio) / 2))."""
+    f = np.float32
+    ratio = max(f(w) / f(tw), f(h) / f(th))
+    rhf, rwf = f(h) / ratio, f(w) / ratio
+    rh, rw = int(np.floor(rhf)), int(np.floor(rwf))
+    ph = max(0, int(np.floor((f(th) - rhf) / f(2))))
+    pw = max(0, int(np.floor((f(tw) - rwf) / f(2))))
+    return rh, rw, ph, pw
+
+
+def preprocess_image(image_u8: np.ndarray, target=MODEL_IMAGE_SIZE) -> np.ndarray:
+    """vision_transformer_utilities.py:435-447 after the file decode: tf.image.resize_with_pad (bilinear,
+    half_pixel_centers=True, antialias=False; TF resize_bilinear CPU kernel: in = (i + 0.5) * scale - 0.5, lower =
+    max(floor(in), 0), upper = min(ceil(in), size - 1), lerp = in - floor(in); top/bottom lerp in x then y, float32),
+    zero padding, clip to [0, 255], / 127.5, - 1.  PARITY UNPINNED (TF semantics restated, not executed)."""
+    f = np.float32
+    img = np.asarray(image_u8)
+    h, w = img.shape[:2]
+    th, tw = target
+    rh, rw, ph, pw = resize_with_pad_geometry(h, w, th, tw)
+    hs, ws = f(h) / f(rh), f(w) / f(rw)
+    iy = (np.arange(rh, dtype=f) + f(0.5)) * hs - f(0.5)
+    ix = (np.arange(rw, dtype=f) + f(0.5)) * ws - f(0.5)
+    fy, fx = np.floor(iy), np.floor(ix)
+    y0 = np.maximum(fy.astype(np.int64), 0); y1 = np.minimum(np.ceil(iy).astype(np.int64), h - 1)
+    x0 = np.maximum(fx.astype(np.int64), 0); x1 = np.minimum(np.ceil(ix).astype(np.int64), w - 1)
+    ly, lx = (iy - fy)[:, None, None], (ix - fx)[None, :, None]
+    src = img.astype(f)
+    tl, tr = src[y0][:, x0], src[y0][:, x1]
+    bl, br = src[y1][:, x0], src[y1][:, x1]
+    top = tl + (tr - tl) * lx
+    bot = bl + (br - bl) * lx
+    res = top + (bot - top) * ly
+    out = np.zeros((th, tw, 3), f)
+    out[ph:ph + rh, pw:pw + rw] = res
+    out = np.clip(out, 0, 255)
+    return out / f(127.5) - f(1)
+
+
 EPSILON = 1e-8                     # Constants.EPSILON det.py:24
 
 

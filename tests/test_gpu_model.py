@@ -262,3 +262,36 @@ def test_visualize_predictions_draws_the_kept_slots():
     labels[0, 1] = [1, 79, 10.2, 10.2, 10, 10]
     lab = vd.visualize_predictions([(imgs[:1], labels)])
     assert len(lab) == 1 and green(lab[0])[5, 5:15].all()
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (608, 608), (1024, 768), (123, 457), (700, 300), (1, 1), (2000, 3000)])
+def test_preprocess_image_is_bit_exact(shape):
+    """N4: resize_with_pad + clip + /127.5 - 1 from uint8 on the GPU, bit-exact against the float32 oracle."""
+    import torch
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    img = rng.integers(0, 256, size=(*shape, 3), dtype=np.uint8)
+    ref = oracle.preprocess_image(img)
+    got = vd.preprocess_image(img)
+    assert got.shape == (608, 608, 3) and got.dtype == np.float32
+    assert np.array_equal(got, ref)
+    assert vd.resize_with_pad_geometry(*shape, 608, 608) == oracle.resize_with_pad_geometry(*shape, 608, 608)
+    dev = vd.preprocess_image(torch.from_numpy(img).cuda(), target_size=(320, 416))
+    assert np.array_equal(dev.cpu().numpy(), oracle.preprocess_image(img, (320, 416)))
+
+
+def test_image_file_to_detections(tmp_path):
+    """File -> _get_image_tensor_coco -> predict -> visualize, the notebook's prediction path end to end."""
+    from PIL import Image
+    from vision_transformer_detector_b200 import vision_transformer_utilities as vu
+    rng = np.random.default_rng(1)
+    arr = rng.integers(0, 256, size=(360, 500, 3), dtype=np.uint8)
+    path = str(tmp_path / "img.png")
+    Image.fromarray(arr).save(path)
+    tensor, size = vu._get_image_tensor_coco(path)
+    assert size == (360, 500) and tensor.shape == (608, 608, 3)
+    assert np.array_equal(tensor, oracle.preprocess_image(arr))
+    m = vd.create_vision_transformer_detector(seed=1)
+    logits = m.predict(tensor[None])
+    out = vd.visualize_predictions(tensor[None], predictions=logits)
+    assert logits.shape == (1, 17, 6) and out[0].shape == (608, 608, 3)
+    m.close()

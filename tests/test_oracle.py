@@ -139,3 +139,23 @@ def test_iou_calculator_matches_reference_known_answers():
     assert oracle.iou_calculator(same, apart)[0] == 0.0
     touching = np.array([[9.0, 4.0, 5.0, 6.0]], np.float64)      # shares an edge: strict comparison -> no overlap
     assert oracle.iou_calculator(same, touching)[0] == 0.0
+
+
+def test_resize_with_pad_geometry_and_preprocess():
+    """Structural checks of the input-side restatement (TF semantics; parity unpinned): float32 size arithmetic,
+    centred zero padding mapped to -1, identity when no resize is needed, value range."""
+    assert oracle.resize_with_pad_geometry(608, 608, 608, 608) == (608, 608, 0, 0)
+    assert oracle.resize_with_pad_geometry(304, 608, 608, 608) == (304, 608, 152, 0)
+    rh, rw, ph, pw = oracle.resize_with_pad_geometry(480, 640, 608, 608)
+    assert rw in (607, 608) and rh in (455, 456) and pw == 0 and ph in (75, 76)          # the float32 quirk of TF may give 607
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(608, 608, 3), dtype=np.uint8)
+    out = oracle.preprocess_image(img)
+    assert out.dtype == np.float32 and np.array_equal(out, img.astype(np.float32) / np.float32(127.5) - np.float32(1))
+    wide = rng.integers(0, 256, size=(100, 400, 3), dtype=np.uint8)
+    o2 = oracle.preprocess_image(wide)
+    assert o2.shape == (608, 608, 3) and (o2[:100] == -1).all() and (o2[-100:] == -1).all() and o2.min() >= -1 and o2.max() <= 1
+    flat = np.full((50, 70, 3), 200, np.uint8)
+    o3 = oracle.preprocess_image(flat, (64, 64))
+    inside = o3[(o3 != -1).any(axis=-1)]
+    assert np.allclose(inside, 200 / 127.5 - 1, atol=1e-6)

@@ -19,8 +19,10 @@ from .vision_transformer_detector import (  # noqa: F401
 
 from .visualization import COCO_CATEGORY_NAMES, visualize_predictions  # noqa: F401,E402
 
+from .vision_transformer_utilities import preprocess_image, resize_with_pad_geometry  # noqa: F401,E402
+
 __all__ = [
-    "COCO_CATEGORY_NAMES", "visualize_predictions",
+    "COCO_CATEGORY_NAMES", "visualize_predictions", "preprocess_image", "resize_with_pad_geometry",
     "Constants", "DetectionRecords", "DetectorConfig", "VisionTransformerDetector",
     "create_vision_transformer_detector", "decode_predictions", "iou_calculator", "mlp_head", "random_weights",
     "transform_predictions", "transformer_encoder", "transformer_preprocessor", "weight_specs",

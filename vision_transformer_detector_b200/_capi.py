@@ -83,6 +83,9 @@ SYMBOLS = {
     "vitdet_forward": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "vitdet_decode": (C.c_int, [_P, C.c_int, C.POINTER(DecodeParams), C.POINTER(Detections), _P]),
     "vitdet_decode_host": (C.c_int, [_P, C.c_int, C.POINTER(DecodeParams), C.POINTER(Detections)]),
+    "vitdet_preprocess_image": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "vitdet_preprocess_image_host": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int]),
+    "vitdet_resize_with_pad_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "vitdet_iou": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "vitdet_iou_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "vitdet_forward_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),

@@ -740,6 +740,12 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
                         const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st,
                         const ForwardOpts& opts = ForwardOpts()) {
     if (!h || !images || B <= 0) return fail(VITDET_E_INVALID, "forward: bad arguments");
+    {
+        int cur = -1;
+        CU_TRY(cudaGetDevice(&cur));
+        if (cur != h->device)
+            return fail(VITDET_E_INVALID, "forward: the handle lives on device %d but the current CUDA device is %d", h->device, cur);
+    }
     if (mode != VITDET_MODE_BF16 && mode != VITDET_MODE_FP32) return fail(VITDET_E_INVALID, "forward: unknown mode %d", mode);
     for (const WeightSlot& s : h->slots)
         if (!s.set) return fail(VITDET_E_UNSET, "forward: weight '%s' has not been set", s.name.c_str());
@@ -1076,6 +1082,29 @@ int vitdet_iou_host(const float* label_host, const float* pred_host, int64_t R, 
     CU_TRY(cudaMemcpy(b.p, pred_host, nb, cudaMemcpyHostToDevice));
     RC_TRY(vitdet_iou(a.as<float>(), b.as<float>(), R, width, o.as<float>(), nullptr));
     CU_TRY(cudaMemcpy(iou_host, o.p, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vitdet_resize_with_pad_geometry(int h, int w, int th, int tw, int* rh, int* rw, int* ph, int* pw) {
+    if (h <= 0 || w <= 0 || th <= 0 || tw <= 0 || !rh || !rw || !ph || !pw) return fail(VITDET_E_INVALID, "resize_with_pad_geometry: bad arguments");
+    resize_with_pad_geometry(h, w, th, tw, rh, rw, ph, pw);
+    return 0;
+}
+
+int vitdet_preprocess_image(const uint8_t* image_dev, int h, int w, float* out_dev, int th, int tw, void* stream) {
+    if (!image_dev || !out_dev) return fail(VITDET_E_INVALID, "preprocess_image: null pointer");
+    CU_TRY(preprocess_launch(image_dev, h, w, out_dev, th, tw, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int vitdet_preprocess_image_host(const uint8_t* image_host, int h, int w, float* out_host, int th, int tw) {
+    if (!image_host || !out_host || h <= 0 || w <= 0 || th <= 0 || tw <= 0) return fail(VITDET_E_INVALID, "preprocess_image_host: bad arguments");
+    DevBuf in, out;
+    RC_TRY(in.ensure(static_cast<size_t>(h) * w * 3));
+    RC_TRY(out.ensure(static_cast<size_t>(th) * tw * 3 * 4));
+    CU_TRY(cudaMemcpy(in.p, image_host, static_cast<size_t>(h) * w * 3, cudaMemcpyHostToDevice));
+    RC_TRY(vitdet_preprocess_image(in.as<uint8_t>(), h, w, out.as<float>(), th, tw, nullptr));
+    CU_TRY(cudaMemcpy(out_host, out.p, static_cast<size_t>(th) * tw * 3 * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

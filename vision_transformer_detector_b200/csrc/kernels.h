@@ -154,6 +154,9 @@ cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w 
                              int R, int U, const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream);
 cudaError_t decode_launch(const float* logits, int R, const DecodeParams& dp, const DecodeOut& out,
                           cudaStream_t stream);
+// Input side (vision_transformer_utilities.py:435-447): uint8 [h, w, 3] -> resize_with_pad(th, tw) -> clip -> /127.5 - 1, f32 [th, tw, 3].
+void resize_with_pad_geometry(int h, int w, int th, int tw, int* rh, int* rw, int* ph, int* pw);
+cudaError_t preprocess_launch(const uint8_t* image, int h, int w, float* out, int th, int tw, cudaStream_t stream);
 // iou_calculator (det.py:761-875): element-wise IoU of (cx, cy, h, w) boxes in the last four entries of `width`-wide rows.
 cudaError_t iou_launch(const float* label, const float* pred, long long R, int width, float eps, float* iou,
                        cudaStream_t stream);

@@ -350,6 +350,46 @@ iou_kernel(const float* __restrict__ label, const float* __restrict__ pred, long
     iou[r] = __fdiv_rn(inter, __fadd_rn(uni, eps));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Input side ("next" row N4): _get_image_tensor_coco of the reference (vision_transformer_utilities.py:418-449) after
+// the file decode: tf.image.resize_with_pad(image, H, W) (bilinear, half-pixel centres, no antialias, zero padding),
+// tf.clip_by_value(0, 255), / 127.5, - 1.  uint8 HWC in, float32 HWC in [-1, 1] out.  The interpolation follows TF's
+// resize_bilinear CPU kernel term by term (in = (i + 0.5) * scale - 0.5; lower = max(floor(in), 0); upper =
+// min(ceil(in), size - 1); lerp = in - floor(in); top/bottom lerp in x, then in y), without FMA contraction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ img, int h, int w, float* __restrict__ out, int th, int tw, int rh, int rw,
+                  int ph, int pw, float hscale, float wscale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= tw) return;
+    float* o = out + (static_cast<size_t>(y) * tw + x) * 3;
+    const int ry = y - ph, rx = x - pw;
+    if (ry < 0 || ry >= rh || rx < 0 || rx >= rw) {
+        o[0] = -1.f; o[1] = -1.f; o[2] = -1.f;        // zero padding: clip(0) / 127.5 - 1
+        return;
+    }
+    const float in_y = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(ry), 0.5f), hscale), 0.5f);
+    const float in_x = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(rx), 0.5f), wscale), 0.5f);
+    const float fy = floorf(in_y), fx = floorf(in_x);
+    const int y0 = max(static_cast<int>(fy), 0), y1 = min(static_cast<int>(ceilf(in_y)), h - 1);
+    const int x0 = max(static_cast<int>(fx), 0), x1 = min(static_cast<int>(ceilf(in_x)), w - 1);
+    const float ly = __fsub_rn(in_y, fy), lx = __fsub_rn(in_x, fx);
+    const uint8_t* r0 = img + static_cast<size_t>(y0) * w * 3;
+    const uint8_t* r1 = img + static_cast<size_t>(y1) * w * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float tl = r0[x0 * 3 + c], tr = r0[x1 * 3 + c], bl = r1[x0 * 3 + c], br = r1[x1 * 3 + c];
+        const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+        const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+        float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        o[c] = __fsub_rn(__fdiv_rn(v, 127.5f), 1.f);
+    }
+}
+
 template <int LPR, typename T>
 cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b, int M, int D, float eps, T* y,
                         int ldy, cudaStream_t st) {
@@ -417,6 +457,29 @@ cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w,
                              bias, R, U, dp, out);
     return launch_kernel(head_tail_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1,
                          static_cast<const __nv_bfloat16*>(h), ldh, w, bias, R, U, dp, out);
+}
+
+void resize_with_pad_geometry(int h, int w, int th, int tw, int* rh, int* rw, int* ph, int* pw) {
+    // tf.image.resize_with_pad's size arithmetic, in float32 exactly as TF does it (it is why a 640 x 480 image can
+    // come out 607 wide): ratio = max(w / tw, h / th); resized = floor(size / ratio); pad = max(0, floor((target - size / ratio) / 2)).
+    const float fh = static_cast<float>(h), fw = static_cast<float>(w), fth = static_cast<float>(th), ftw = static_cast<float>(tw);
+    const float ratio = fmaxf(fw / ftw, fh / fth);
+    const float rhf = fh / ratio, rwf = fw / ratio;
+    *rh = static_cast<int>(floorf(rhf));
+    *rw = static_cast<int>(floorf(rwf));
+    const int p_h = static_cast<int>(floorf((fth - rhf) / 2.f)), p_w = static_cast<int>(floorf((ftw - rwf) / 2.f));
+    *ph = p_h > 0 ? p_h : 0;
+    *pw = p_w > 0 ? p_w : 0;
+}
+
+cudaError_t preprocess_launch(const uint8_t* image, int h, int w, float* out, int th, int tw, cudaStream_t stream) {
+    if (h <= 0 || w <= 0 || th <= 0 || tw <= 0) return cudaErrorInvalidValue;
+    int rh, rw, ph, pw;
+    resize_with_pad_geometry(h, w, th, tw, &rh, &rw, &ph, &pw);
+    if (rh <= 0 || rw <= 0) return cudaErrorInvalidValue;
+    const float hscale = static_cast<float>(h) / static_cast<float>(rh), wscale = static_cast<float>(w) / static_cast<float>(rw);
+    dim3 grid((tw + 255) / 256, th);
+    return launch_kernel(preprocess_kernel, grid, dim3(256), 0, stream, 1, image, h, w, out, th, tw, rh, rw, ph, pw, hscale, wscale);
 }
 
 cudaError_t iou_launch(const float* label, const float* pred, long long R, int width, float eps, float* iou,
