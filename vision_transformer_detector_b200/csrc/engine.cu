@@ -225,8 +225,6 @@ struct BlockW {
     std::vector<DenseW> mlp;
 };
 
-struct PlanSet;   // per (mode, rows) cached TMA descriptors
-
 }  // namespace vitdet
 
 using namespace vitdet;
@@ -257,8 +255,7 @@ struct vitdet_handle {
     // cached plans
     struct EncPlans {
         bool valid = false;
-        const void* base_sig[8] = {};
-        TcGemmPlan proj, head_dummy;
+        TcGemmPlan proj;
         std::vector<TcGemmPlan> qkv, out;
         std::vector<std::vector<TcGemmPlan>> mlp;
         std::vector<AttnPlan> attn;
@@ -268,7 +265,6 @@ struct vitdet_handle {
     std::map<int, EncPlans> enc_plans;      // key: images in the chunk
     struct HeadPlans {
         bool valid = false;
-        const void* base_sig[4] = {};
         std::vector<TcGemmPlan> dense;
     };
     std::map<int, HeadPlans> head_plans;    // key: batch
