@@ -295,3 +295,36 @@ def test_image_file_to_detections(tmp_path):
     out = vd.visualize_predictions(tensor[None], predictions=logits)
     assert logits.shape == (1, 17, 6) and out[0].shape == (608, 608, 3)
     m.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] size (default config, batch 64, bf16), checked through size-independent properties: images
+    are independent, so the result must be bit-identical under a permutation of the batch, under any split into
+    sub-batches / encoder chunks, across repeated runs, and between the host-buffer path (staged H2D, lead chunks of
+    4 / 12 images) and the device-tensor path (one chunk of 64).  A 3-image slice is also compared with the oracle."""
+    import torch
+    cfg = vd.DetectorConfig()
+    w = vd.random_weights(cfg, seed=1, spread=True)
+    m = build_model(cfg, w, "bf16")
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    x = torch.rand((64, *cfg.input_shape), generator=g, device="cuda") * 2 - 1
+    rec = m.detect(x)
+    base = rec.logits.cpu().numpy()
+    assert np.isfinite(base).all()
+    assert np.array_equal(m(x).cpu().numpy(), base)                                   # deterministic
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(3))
+    assert np.array_equal(m(x[perm.cuda()]).cpu().numpy(), base[perm.numpy()])        # permutation-equivariant
+    assert np.array_equal(m(x[10:37]).cpu().numpy(), base[10:37])                     # any sub-batch
+    host = m.detect(x.cpu().numpy())                                                  # predict_host: staged copy + lead chunks
+    assert np.array_equal(host.logits, base)
+    assert np.array_equal(host.keep, rec.keep.cpu().numpy()) and np.array_equal(host.corners, rec.corners.cpu().numpy())
+    m.set_chunk(24)                                                                   # 24 + 24 + 16
+    assert np.array_equal(m(x).cpu().numpy(), base)
+    ref = oracle.forward_torch_f32(w, cfg, x[:3].cpu().numpy())
+    assert rel_err(base[:3], ref) < TOL_BF16
+    # decode of the full batch: ids / keep / corners recomputed by the oracle from the GPU's own decoded floats
+    dec = rec.decoded.cpu().numpy()
+    cid, cc, keep = oracle.threshold(dec)
+    assert np.array_equal(rec.class_id.cpu().numpy(), cid) and np.array_equal(rec.keep.cpu().numpy().astype(bool), keep)
+    assert np.array_equal(rec.corners.cpu().numpy(), oracle.corners(dec, cfg.input_shape[:2]))
+    m.close()
