@@ -178,6 +178,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local_rank: int):
+    """Pins this rank to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the pinned
+    host buffers it allocates next are first-touched on the GPU's NUMA node: with 8 ranks each copying 568 MB per step
+    the H2D path otherwise crosses the socket interconnect.  Best effort; returns the cpu list or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -195,9 +215,22 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints a version banner on STDOUT when the communicator is created: send fd 1 to stderr until the
+        # first collective has run, so that stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     cfg, desc = variant_config(vd, args.variant)
     if args.batch_per_gpu:
@@ -287,16 +320,18 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * args.steps / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(world * B * np.prod(cfg.input_shape) * 4),
-               "d2h_bytes_per_step": int(world * B * (S * 24 + rec_bytes))}
+               "d2h_bytes_per_step": int(world * B * (S * 24 + rec_bytes)),
+               "host_affinity": (f"{len(numa_cpus)} cpus local to the GPU" if numa_cpus else "unbound")}
 
     # ---- roofline of the dominant kernel (the 3584 -> 1792 MLP GEMM in the default config) ----
     roofline = None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak_tf, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
+    peak_tf, peak_src, pk_burst = 1590.0, "fallback (B200_PROFILING.md)", 1590.0
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
         # the kernel is timed inside a long step -> sustained figure
         peak_tf, peak_src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured sustained (MEASURED_PEAKS.json)"
+        pk_burst = float(pk.get("bf16_tflops", peak_tf))
     if dominant in prof and args.mode == "bf16":
         ms_k, n_k = prof[dominant]
         units = cfg.encoder_mlp_units()
@@ -311,7 +346,7 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")      # from the committed ncu --set full capture
         roofline = {"bound": "tensor", "kernel": f"{'gemm_tc2_kernel (CTA pair)' if K_ >= 512 and N_ >= 128 else 'gemm_tc_kernel'}[{dominant}: K={K_} -> N={N_}, bias+Mish epilogue]",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src, "launches": n_k, "avg_launch_ms": ms_k / n_k,
+                    "peak_source": peak_src, "peak_burst": pk_burst, "frac_of_burst": (achieved / pk_burst if pk_burst else None), "launches": n_k, "avg_launch_ms": ms_k / n_k,
                     "share_of_step": ms_k / (ms_step * args.steps), "traffic": traffic,
                     "algorithmic_bytes": 2.0 * (B * cfg.tokens * (K_ + N_) + K_ * N_)}
 
