@@ -190,6 +190,53 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
                         const vitdet_decode_params* params, float* logits_host,
                         const vitdet_detections* out_host, void* stream);
 
+/* ---- evaluation metric ("next" row N2): MeanAveragePrecision of the reference (det.py:1268-2060) ----
+ * The COCO-style AP of the reference: mean over the IoU thresholds tf.linspace(0.5, 0.95, 10) of the mean, over the
+ * classes seen so far, of the class AP computed from the latest `latest_related_images` related images per class
+ * with at most `bboxes_per_image` (confidence, IoU) rows each.  The three state tensors of the reference
+ * (latest_positive_bboxes, labels_quantity_per_image, showed_up_classes; det.py:1286-1305) live on the device that
+ * is current when vitdet_map_create is called. */
+typedef struct vitdet_map vitdet_map;
+
+/* MeanAveragePrecision.__init__ (det.py:1280-1308).  The reference's constants are classes = 80,
+ * latest_related_images = 3 (Constants.LATEST_RELATED_IMAGES, det.py:32), bboxes_per_image = 14
+ * (Constants.BBOXES_PER_IMAGE, det.py:37). */
+int vitdet_map_create(int classes, int latest_related_images, int bboxes_per_image, vitdet_map** out);
+void vitdet_map_destroy(vitdet_map* m);
+
+/* reset_state (det.py:2052-2060): zero the three state tensors.  Asynchronous on `stream`. */
+int vitdet_map_reset(vitdet_map* m, void* stream);
+
+/* update_state(y_true, y_pred, use_transform_predictions) (det.py:1310-1862).  y_true_dev, y_pred_dev: DEVICE
+ * float32 [batch, slots, 6] rows (objectness, class, cx, cy, h, w): labels as the reference builds them (empty
+ * slots hold objectness 0 and -8 elsewhere), predictions either raw head outputs
+ * (params->use_transform_predictions = 1: transform_predictions is applied first, using params->image_h/w and
+ * params->classes) or already decoded rows (0).  Uses params->objectness_threshold / classification_threshold with
+ * the metric's strict '>' rule (params->strict and corner_scale are ignored).  The images of the batch are taken
+ * in order, as the reference's `for sample in range(batch_size)` does.  Asynchronous on `stream`; y_pred_dev can be
+ * the logits buffer vitdet_forward just wrote on the same stream. */
+int vitdet_map_update(vitdet_map* m, const float* y_true_dev, const float* y_pred_dev, int batch, int slots,
+                      const vitdet_decode_params* params, void* stream);
+/* Same with HOST arrays; copies in, updates, synchronises. */
+int vitdet_map_update_host(vitdet_map* m, const float* y_true_host, const float* y_pred_host, int batch, int slots,
+                           const vitdet_decode_params* params);
+
+/* result() (det.py:1865-2049).  HOST outputs: *mean_ap; per_iou_host[10] (AP averaged over the seen classes, per
+ * IoU threshold; may be NULL); per_class_host[10 * classes] (AP per threshold and class, 0 for classes not seen;
+ * may be NULL).  Runs on `stream` and synchronises it. */
+int vitdet_map_result(vitdet_map* m, float* mean_ap_host, float* per_iou_host, float* per_class_host, void* stream);
+
+/* The state in the reference's layout, to HOST arrays (any may be NULL): latest_positive_bboxes
+ * [classes, latest_related_images, bboxes_per_image, 2] f32, labels_quantity_per_image
+ * [classes, latest_related_images] f32, showed_up_classes [classes] u8 (0/1).  Synchronises `stream`. */
+int vitdet_map_state(vitdet_map* m, float* bboxes_host, float* labels_host, uint8_t* showed_host, void* stream);
+
+/* The ten float32 IoU thresholds result() uses (tf.linspace(0.5, 0.95, num=10), det.py:1876). */
+int vitdet_map_iou_thresholds(const vitdet_map* m, float* out10);
+
+/* Number of kernels this metric object has launched so far. */
+uint64_t vitdet_map_launch_count(const vitdet_map* m);
+
 /* ---- operator-level entry points (the Keras layers the path is built from; used by the parity
  * tests to check each kernel against the oracle in isolation).  All pointers are DEVICE pointers. ---- */
 

@@ -40,3 +40,43 @@ def build_model(cfg, weights, compute_mode="bf16"):
     m = VisionTransformerDetector(cfg, seed=None, compute_mode=compute_mode)
     m.set_weights(weights)
     return m
+
+
+def map_case(seed, batch, slots, classes_used=(3, 17, 79), exact_class=0.5, max_labels=6, max_extra=6, image=608.0):
+    """Seeded (y_true, y_pred) pair of already-decoded (batch, slots, 6) rows for the evaluation metric: per image a few
+    labelled boxes of a few classes, predictions that jitter the labels (so IoUs land on both sides of 0.5 and of the
+    ten thresholds), spurious predictions, sub-threshold ones, and class values either exactly on an integer
+    (equal confidences -> the tie rule matters) or off by up to 0.3 (confidence below / above 0.5)."""
+    rng = np.random.default_rng(seed)
+    y_true = np.full((batch, slots, 6), -8.0, np.float32)
+    y_true[..., 0] = 0
+    y_pred = np.zeros((batch, slots, 6), np.float32)
+    y_pred[..., 1] = rng.uniform(0, 79, (batch, slots))
+    y_pred[..., 2:] = rng.uniform(0, image, (batch, slots, 4))
+    y_pred[..., 0] = rng.uniform(0, 0.5, (batch, slots))          # not positive unless overwritten below
+    for b in range(batch):
+        nl = int(rng.integers(0, min(max_labels, slots) + 1))
+        label_slots = rng.choice(slots, nl, replace=False)
+        free = [s for s in rng.permutation(slots)]
+        for s in label_slots:
+            c = float(rng.choice(classes_used))
+            box = [rng.uniform(50, image - 50), rng.uniform(50, image - 50), rng.uniform(20, 200), rng.uniform(20, 200)]
+            if rng.random() < 0.2:
+                box[2:] = [64.0, 64.0]                             # equal areas: the stable-sort rule decides
+            y_true[b, s] = [1.0, c, *box]
+            if rng.random() < 0.8 and free:                        # a prediction near this label
+                ps = free.pop()
+                jitter = rng.choice([0.0, 0.02, 0.1, 0.25, 0.6])
+                pbox = [box[0] + rng.normal() * jitter * box[3], box[1] + rng.normal() * jitter * box[2],
+                        box[2] * (1 + rng.normal() * jitter * 0.5), box[3] * (1 + rng.normal() * jitter * 0.5)]
+                cls = c if rng.random() < exact_class else c + rng.uniform(-0.3, 0.3)
+                y_pred[b, ps] = [rng.uniform(0.4, 1.0), np.clip(cls, 0, 79), *np.clip(pbox, 0, image)]
+        for _ in range(int(rng.integers(0, max_extra + 1))):       # predictions with no label behind them
+            if not free:
+                break
+            ps = free.pop()
+            c = float(rng.choice(classes_used))
+            cls = c if rng.random() < exact_class else c + rng.uniform(-0.3, 0.3)
+            y_pred[b, ps] = [rng.uniform(0.4, 1.0), np.clip(cls, 0, 79), rng.uniform(0, image), rng.uniform(0, image),
+                             rng.uniform(10, 200), rng.uniform(10, 200)]
+    return y_true, y_pred

@@ -5,6 +5,7 @@ from .vision_transformer_detector import (  # noqa: F401
     Constants,
     DetectionRecords,
     DetectorConfig,
+    MeanAveragePrecision,
     VisionTransformerDetector,
     create_vision_transformer_detector,
     decode_predictions,
@@ -23,7 +24,7 @@ from .vision_transformer_utilities import preprocess_image, resize_with_pad_geom
 
 __all__ = [
     "COCO_CATEGORY_NAMES", "visualize_predictions", "preprocess_image", "resize_with_pad_geometry",
-    "Constants", "DetectionRecords", "DetectorConfig", "VisionTransformerDetector",
+    "Constants", "DetectionRecords", "DetectorConfig", "MeanAveragePrecision", "VisionTransformerDetector",
     "create_vision_transformer_detector", "decode_predictions", "iou_calculator", "mlp_head", "random_weights",
     "transform_predictions", "transformer_encoder", "transformer_preprocessor", "weight_specs",
 ]

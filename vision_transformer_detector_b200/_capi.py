@@ -88,6 +88,15 @@ SYMBOLS = {
     "vitdet_resize_with_pad_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "vitdet_iou": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "vitdet_iou_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "vitdet_map_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vitdet_map_destroy": (None, [_P]),
+    "vitdet_map_reset": (C.c_int, [_P, _P]),
+    "vitdet_map_update": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P]),
+    "vitdet_map_update_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams)]),
+    "vitdet_map_result": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vitdet_map_state": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vitdet_map_iou_thresholds": (C.c_int, [_P, _P]),
+    "vitdet_map_launch_count": (C.c_uint64, [_P]),
     "vitdet_forward_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),
     "vitdet_predict_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),
     "vitdet_op_dense": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

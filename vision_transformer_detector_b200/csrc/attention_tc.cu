@@ -335,12 +335,8 @@ cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream) {
     a.k16 = (d.d + 15) / 16;
     a.scale_log2 = d.scale * 1.4426950408889634f;
     const size_t smem = static_cast<size_t>(kQBytes) + static_cast<size_t>(kStages) * 2 * kTileBytes;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc_kernel), static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
     dim3 grid((d.T + kQ - 1) / kQ, d.B * d.H);
     return launch_kernel(attn_tc_kernel, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
 }

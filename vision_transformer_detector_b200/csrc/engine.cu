@@ -30,6 +30,7 @@
 
 #include "../../include/vitdet_b200.h"
 #include "common.cuh"
+#include "devbuf.h"
 #include "kernels.h"
 
 namespace vitdet {
@@ -39,26 +40,13 @@ namespace vitdet {
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-
-#define CU_TRY(expr)                                                                               \
-    do {                                                                                           \
-        cudaError_t e__ = (expr);                                                                  \
-        if (e__ != cudaSuccess)                                                                    \
-            return fail(VITDET_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-#define RC_TRY(expr)                   \
-    do {                               \
-        int rc__ = (expr);             \
-        if (rc__ != 0) return rc__;    \
-    } while (0)
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -150,36 +138,6 @@ __global__ void unpack_ctx_kernel(const T* __restrict__ ctx, long long rows, int
 }
 
 static inline int blocks_for(long long n, int bs = 256) { return static_cast<int>((n + bs - 1) / bs); }
-
-// ------------------------------------------------------------------------------------------------
-// device buffer helper
-// ------------------------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) {
-            if (p) cudaFree(p);
-            p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0;
-        }
-        return *this;
-    }
-    int ensure(size_t need) {
-        if (need <= bytes) return 0;
-        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
-        need = (need + 255) / 256 * 256;
-        cudaError_t e = cudaMalloc(&p, need);
-        if (e != cudaSuccess) return fail(VITDET_E_CUDA, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
-        bytes = need;
-        return 0;
-    }
-    template <typename T> T* as() const { return static_cast<T*>(p); }
-};
 
 // ------------------------------------------------------------------------------------------------
 // weights

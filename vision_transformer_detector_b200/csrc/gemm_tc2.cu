@@ -298,11 +298,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int ACT, bool OUT_F32>
 cudaError_t launch_variant2(const TcGemmPlan& plan, const Tc2GemmArgs& a, cudaStream_t stream) {
     auto kern = gemm_tc2_kernel<ACT, OUT_F32>;
-    static bool attr_done = false;   // per template instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    {
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), kMaxDynSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     return launch_kernel(kern, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, 2, plan.tmA, plan.tmB, plan.tmC, a);
 }

@@ -161,4 +161,7 @@ cudaError_t preprocess_launch(const uint8_t* image, int h, int w, float* out, in
 cudaError_t iou_launch(const float* label, const float* pred, long long R, int width, float eps, float* iou,
                        cudaStream_t stream);
 
+// Records the message vitdet_last_error() returns on the calling thread and hands `code` back (engine.cu).
+int fail(int code, const char* fmt, ...);
+
 }  // namespace vitdet

@@ -10,6 +10,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <utility>
 
 namespace vitdet {
@@ -18,6 +20,22 @@ inline bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("VITDET_PDL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
     return v == 1;
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory, once per (kernel, device): the attribute is per device, and a
+// process may drive more than one.
+inline cudaError_t ensure_max_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<const void*, unsigned long long> done;      // kernel -> bitmask of devices already configured
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long& mask = done[kernel];
+    if (dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) mask |= 1ull << dev;
+    return e;
 }
 
 template <typename... KArgs, typename... Args>

@@ -308,11 +308,9 @@ int mlp_tail_make_plan(MlpTailPlan* plan, const MlpTailDesc& d, int num_sms) {
 template <int ACT>
 static cudaError_t tail_launch_variant(const MlpTailPlan& plan, const TailMaps& maps, const TailArgs& a, cudaStream_t stream) {
     auto kern = mlp_tail_kernel<ACT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    {
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), 224 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     return launch_kernel(kern, dim3(plan.grid), dim3(kTailThreads), plan.smem_bytes, stream, 1, maps, a);
 }

@@ -2,6 +2,7 @@
 // projection, and the fused head tail (Dense(U->6) + sigmoid + clip + scale + thresholds).
 // All of them are HBM/L2 streaming kernels: coalesced 16-byte accesses where the layout allows it,
 // warp-shuffle reductions, no shared-memory staging (there is no reuse to exploit).
+#include "boxops.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -211,35 +212,19 @@ head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Decode of one slot: transform_predictions (det.py:619-645) + thresholds + corner boxes.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_f32(float x) { return 1.f / (1.f + expf(-x)); }
-
-// tf.clip_by_value(x, 0, 1) = minimum(maximum(x, 0), 1); TF's maximum/minimum propagate NaN.
-__device__ __forceinline__ float clip01_nan(float x) { return (x != x) ? x : fminf(fmaxf(x, 0.f), 1.f); }
-
 __device__ __forceinline__ int clip_int(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ void decode_slot(const float (&l)[6], long long r, const DecodeParams& dp,
                                             const DecodeOut& o) {
     float dec[6];
     if (dp.apply_transform) {
-        float s[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) s[j] = sigmoid_f32(l[j]);
-#pragma unroll
-        for (int j = 2; j < 6; ++j) s[j] = clip01_nan(s[j]);
-        dec[0] = s[0];
-        dec[1] = s[1] * static_cast<float>(dp.classes - 1);
-        dec[2] = s[2] * dp.img_w;   // center_x   (det.py:637)
-        dec[3] = s[3] * dp.img_h;   // center_y   (det.py:638)
-        dec[4] = s[4] * dp.img_h;   // bbox_height(det.py:639)
-        dec[5] = s[5] * dp.img_w;   // bbox_width (det.py:640)
+        transform_slot(l, dp, dec);
     } else {
 #pragma unroll
         for (int j = 0; j < 6; ++j) dec[j] = l[j];
     }
     const float id = rintf(dec[1]);                 // tf.round / np.round: half to even
-    const float err = fabsf(dec[1] - id);
-    const float cc = (0.5f - err) / 0.5f;           // det.py:1376, 2279
+    const float cc = class_confidence(dec[1]);      // det.py:1376, 2279
     bool keep;
     if (dp.strict) keep = (dec[0] > dp.obj_thr) && (cc > dp.cls_thr);        // det.py:1381-1384
     else keep = !(dec[0] < dp.obj_thr) && !(cc < dp.cls_thr);               // det.py:2264, 2282
@@ -321,13 +306,6 @@ decode_kernel(const float* __restrict__ logits, int R, DecodeParams dp, DecodeOu
 // overlap test, the two middle values of the four sorted edges, I / (U + eps)); __f*_rn intrinsics keep the
 // compiler from contracting products and sums into FMAs, so the result is bit-identical to an f32 evaluation.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sort2(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
-
-__device__ __forceinline__ float middle_extent(float a, float b, float c, float d) {
-    sort2(a, b); sort2(c, d); sort2(a, c); sort2(b, d); sort2(b, c);      // a <= b <= c <= d
-    return __fsub_rn(c, b);                                                // sorted[-2] - sorted[-3]
-}
-
 __global__ void __launch_bounds__(256)
 iou_kernel(const float* __restrict__ label, const float* __restrict__ pred, long long R, int width, float eps,
            float* __restrict__ iou) {
@@ -339,15 +317,7 @@ iou_kernel(const float* __restrict__ label, const float* __restrict__ pred, long
     const float* pb = pred + r * width + (width - 4);
     const float lx = lb[0], ly = lb[1], lh = lb[2], lw = lb[3];
     const float px = pb[0], py = pb[1], ph = pb[2], pw = pb[3];
-    const float l_left = __fsub_rn(lx, __fmul_rn(lw, 0.5f)), l_right = __fadd_rn(lx, __fmul_rn(lw, 0.5f));
-    const float p_left = __fsub_rn(px, __fmul_rn(pw, 0.5f)), p_right = __fadd_rn(px, __fmul_rn(pw, 0.5f));
-    const float l_top = __fsub_rn(ly, __fmul_rn(lh, 0.5f)), l_bottom = __fadd_rn(ly, __fmul_rn(lh, 0.5f));
-    const float p_top = __fsub_rn(py, __fmul_rn(ph, 0.5f)), p_bottom = __fadd_rn(py, __fmul_rn(ph, 0.5f));
-    const bool hit = (l_left < p_right) && (l_right > p_left) && (l_top < p_bottom) && (l_bottom > p_top);
-    float inter = 0.f;
-    if (hit) inter = __fmul_rn(middle_extent(l_top, l_bottom, p_top, p_bottom), middle_extent(l_left, l_right, p_left, p_right));
-    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(pw, ph), __fmul_rn(lw, lh)), inter);
-    iou[r] = __fdiv_rn(inter, __fadd_rn(uni, eps));
+    iou[r] = iou_boxes(lx, ly, lh, lw, px, py, ph, pw, eps);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -354,6 +354,126 @@ def iou_calculator(label_bbox, prediction_bbox):
 
 
 # ------------------------------------------------------------------------------------------------
+# evaluation metric
+# ------------------------------------------------------------------------------------------------
+class MeanAveragePrecision:
+    """det.py:1268-2060 (tf.keras.metrics.Metric in the reference): the COCO-style AP — mean over ten IoU
+    thresholds of the mean class AP — over the latest LATEST_RELATED_IMAGES related images per class with at most
+    BBOXES_PER_IMAGE (confidence, IoU) rows each.  State and arithmetic live on the GPU (csrc/metric.cu); the three
+    state attributes of the reference are exposed as read-only numpy copies in the reference's layout.
+
+    update_state takes numpy arrays or torch CUDA tensors of shape (batch, slots, 6); with torch CUDA tensors nothing
+    leaves the device, so `metric.update_state(labels, model(images))` evaluates straight from the head's output.
+    """
+
+    def __init__(self, name: str = "AP", classes: int | None = None, latest_related_images: int | None = None,
+                 bboxes_per_image: int | None = None, image_size=None, **kwargs):
+        self.name = name
+        self.classes = Constants.CLASSES.value if classes is None else int(classes)
+        self.latest_related_images = Constants.LATEST_RELATED_IMAGES.value if latest_related_images is None else int(latest_related_images)
+        self.bboxes_per_image = Constants.BBOXES_PER_IMAGE.value if bboxes_per_image is None else int(bboxes_per_image)
+        self.image_size = tuple(Constants.MODEL_IMAGE_SIZE.value if image_size is None else image_size)
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        _capi.check(self._lib.vitdet_map_create(self.classes, self.latest_related_images, self.bboxes_per_image, C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.vitdet_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _params(self, use_transform_predictions: bool) -> _capi.DecodeParams:
+        p = _decode_params(None, None, True, self.image_size, use_transform_predictions)
+        p.classes = self.classes
+        return p
+
+    def update_state(self, y_true, y_pred, sample_weight=None, use_transform_predictions=True) -> None:
+        """det.py:1310-1862.  `sample_weight` is accepted and ignored, as in the reference."""
+        p = self._params(bool(use_transform_predictions))
+        if _is_torch_cuda(y_true) or _is_torch_cuda(y_pred):
+            import torch
+            dev = y_pred.device if _is_torch_cuda(y_pred) else y_true.device
+            a = torch.as_tensor(y_true).to(device=dev, dtype=torch.float32).contiguous()
+            b = torch.as_tensor(y_pred).to(device=dev, dtype=torch.float32).contiguous()
+            if a.ndim != 3 or a.shape[-1] != 6 or a.shape != b.shape:
+                raise ValueError(f"y_true {tuple(a.shape)} and y_pred {tuple(b.shape)} must both be (batch, slots, 6)")
+            with torch.cuda.device(dev):
+                _capi.check(self._lib.vitdet_map_update(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), int(a.shape[0]),
+                                                        int(a.shape[1]), C.byref(p), _torch_stream_ptr(dev)))
+            # the kernels read a / b asynchronously on the current stream; torch's caching allocator only reuses their
+            # memory for work queued later on that same stream, so letting them go out of scope here is safe
+            return
+        a = np.ascontiguousarray(np.asarray(y_true, dtype=np.float32))
+        b = np.ascontiguousarray(np.asarray(y_pred, dtype=np.float32))
+        if a.ndim != 3 or a.shape[-1] != 6 or a.shape != b.shape:
+            raise ValueError(f"y_true {a.shape} and y_pred {b.shape} must both be (batch, slots, 6)")
+        _capi.check(self._lib.vitdet_map_update_host(self._h, _capi.np_ptr(a), _capi.np_ptr(b), int(a.shape[0]), int(a.shape[1]), C.byref(p)))
+
+    def _result(self):
+        mean = np.zeros(1, np.float32)
+        per_iou = np.zeros(10, np.float32)
+        per_class = np.zeros((10, self.classes), np.float32)
+        _capi.check(self._lib.vitdet_map_result(self._h, _capi.np_ptr(mean), _capi.np_ptr(per_iou), _capi.np_ptr(per_class), self._stream()))
+        return mean[0], per_iou, per_class
+
+    def result(self) -> np.float32:
+        """det.py:1865-2049: the mean average precision as a float32 scalar."""
+        return self._result()[0]
+
+    def average_precision_per_iou(self) -> np.ndarray:
+        """AP averaged over the classes seen so far, one value per IoU threshold (det.py:2024-2045)."""
+        return self._result()[1]
+
+    def average_precisions(self) -> np.ndarray:
+        """(10, classes) AP per IoU threshold and class; classes that never showed up hold 0 (det.py:1879-2022)."""
+        return self._result()[2]
+
+    def reset_state(self) -> None:
+        """det.py:2052-2060."""
+        _capi.check(self._lib.vitdet_map_reset(self._h, self._stream()))
+
+    reset_states = reset_state      # keras' older spelling
+
+    def _stream(self) -> C.c_void_p:
+        import torch
+        return _torch_stream_ptr(torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else C.c_void_p()
+
+    def _state(self):
+        bboxes = np.zeros((self.classes, self.latest_related_images, self.bboxes_per_image, 2), np.float32)
+        labels = np.zeros((self.classes, self.latest_related_images), np.float32)
+        showed = np.zeros((self.classes,), np.uint8)
+        _capi.check(self._lib.vitdet_map_state(self._h, _capi.np_ptr(bboxes), _capi.np_ptr(labels), _capi.np_ptr(showed), self._stream()))
+        return bboxes, labels, showed.astype(bool)
+
+    @property
+    def latest_positive_bboxes(self) -> np.ndarray:          # det.py:1286-1292
+        return self._state()[0]
+
+    @property
+    def labels_quantity_per_image(self) -> np.ndarray:       # det.py:1296-1299
+        return self._state()[1]
+
+    @property
+    def showed_up_classes(self) -> np.ndarray:               # det.py:1303-1305
+        return self._state()[2]
+
+    @property
+    def iou_thresholds(self) -> np.ndarray:
+        out = np.zeros(10, np.float32)
+        _capi.check(self._lib.vitdet_map_iou_thresholds(self._h, _capi.np_ptr(out)))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.vitdet_map_launch_count(self._h))
+
+
+# ------------------------------------------------------------------------------------------------
 # the model object
 # ------------------------------------------------------------------------------------------------
 class Weight:
