@@ -97,21 +97,29 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
         l *= alpha;
     }
     const float neg_m = -m_used;
-    float sum[4] = {0.f, 0.f, 0.f, 0.f};
-    // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers
+    // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers.  The scale-and-shift
+    // and the row sums run on packed float pairs (FFMA2 / FADD2: one issue slot for two elements).
+    const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_m, neg_m);
+    uint64_t sum2[2] = {0ull, 0ull};       // two (0.f, 0.f) pairs
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-            const float e0 = ex2f(fmaf(__uint_as_float(v[c][i]), scale_log2, neg_m));      // ex2(-inf) = 0
-            const float e1 = ex2f(fmaf(__uint_as_float(v[c][i + 1]), scale_log2, neg_m));
-            const float e2 = ex2f(fmaf(__uint_as_float(v[c][i + 2]), scale_log2, neg_m));
-            const float e3 = ex2f(fmaf(__uint_as_float(v[c][i + 3]), scale_log2, neg_m));
-            sum[0] += e0; sum[1] += e1; sum[2] += e2; sum[3] += e3;
+            float t0, t1, t2, t3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), t0, t1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])), sc2, nm2), t2, t3);
+            const float e0 = ex2f(t0), e1 = ex2f(t1), e2 = ex2f(t2), e3 = ex2f(t3);      // ex2(-inf) = 0
+            sum2[0] = f2_add(sum2[0], f2_pack(e0, e1));
+            sum2[1] = f2_add(sum2[1], f2_pack(e2, e3));
             v[c][i / 2] = pack_bf16x2(e0, e1);
             v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
         }
-    l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    {
+        float s0, s1, s2, s3;
+        f2_unpack(sum2[0], s0, s1);
+        f2_unpack(sum2[1], s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+    }
 
     // P and O must no longer be in use by PV(j-1)
     if (j > 0) {

@@ -68,6 +68,59 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed float32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on an aligned register pair, one issue slot for two
+// lanes of arithmetic).  The epilogues are issue-bound (profiles/r01c_ncu_gemm_mlp1.md), so the bias add and the
+// five FMA-pipe steps of Mish are done on pairs: 4.5 instead of 7 instructions per element, same roundings.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// mish<false> on a pair (same operations and roundings as the scalar form above).
+__device__ __forceinline__ uint64_t mish2_fast(uint64_t x) {
+    float t0, t1, n0, n1, q0, q1, r0, r1;
+    f2_unpack(f2_mul(x, f2_pack(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n1) : "f"(t1));
+    const uint64_t two = f2_pack(2.f, 2.f), n = f2_pack(n0, n1);
+    f2_unpack(f2_fma(n, f2_add(n, two), two), q0, q1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
+    return f2_fma(f2_mul(x, f2_pack(-2.f, -2.f)), f2_pack(r0, r1), x);
+}
+
+// act(a + b) for two neighbouring columns, rounded to a packed bf16 pair (the epilogues' inner step).
+template <int ACT>
+__device__ __forceinline__ uint32_t bias_act_bf16x2(float a0, float a1, float b0, float b1) {
+    if (ACT == ACT_MISH) {
+        float y0, y1;
+        f2_unpack(mish2_fast(f2_add(f2_pack(a0, a1), f2_pack(b0, b1))), y0, y1);
+        return pack_bf16x2(y0, y1);
+    }
+    return pack_bf16x2(apply_act<ACT, false>(a0 + b0), apply_act<ACT, false>(a1 + b1));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (see launch.h)
 // ---------------------------------------------------------------------------------------------
 // Lets the next kernel of the stream start its prologue; call as early as possible.

@@ -279,12 +279,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float y0 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 0]) + b4.x);
-                            const float y1 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 1]) + b4.y);
-                            const float y2 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 2]) + b4.z);
-                            const float y3 = apply_act<ACT, false>(__uint_as_float(v[4 * g + 3]) + b4.w);
-                            o[2 * g] = pack_bf16x2(y0, y1);
-                            o[2 * g + 1] = pack_bf16x2(y2, y3);
+                            o[2 * g] = bias_act_bf16x2<ACT>(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1]), b4.x, b4.y);
+                            o[2 * g + 1] = bias_act_bf16x2<ACT>(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]), b4.z, b4.w);
                         }
                     } else {      // last N tile: columns >= N are written as zero
 #pragma unroll

@@ -160,14 +160,10 @@ mlp_tail_kernel(const __grid_constant__ TailMaps maps, const TailArgs p) {
                         for (int g = 0; g < 4; ++g) {
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g));
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * g + 4));
-                            const uint32_t o0 = pack_bf16x2(apply_act<ACT, false>(__uint_as_float(v[8 * g + 0]) + b0.x),
-                                                            apply_act<ACT, false>(__uint_as_float(v[8 * g + 1]) + b0.y));
-                            const uint32_t o1 = pack_bf16x2(apply_act<ACT, false>(__uint_as_float(v[8 * g + 2]) + b0.z),
-                                                            apply_act<ACT, false>(__uint_as_float(v[8 * g + 3]) + b0.w));
-                            const uint32_t o2 = pack_bf16x2(apply_act<ACT, false>(__uint_as_float(v[8 * g + 4]) + b1.x),
-                                                            apply_act<ACT, false>(__uint_as_float(v[8 * g + 5]) + b1.y));
-                            const uint32_t o3 = pack_bf16x2(apply_act<ACT, false>(__uint_as_float(v[8 * g + 6]) + b1.z),
-                                                            apply_act<ACT, false>(__uint_as_float(v[8 * g + 7]) + b1.w));
+                            const uint32_t o0 = bias_act_bf16x2<ACT>(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), b0.x, b0.y);
+                            const uint32_t o1 = bias_act_bf16x2<ACT>(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]), b0.z, b0.w);
+                            const uint32_t o2 = bias_act_bf16x2<ACT>(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]), b1.x, b1.y);
+                            const uint32_t o3 = bias_act_bf16x2<ACT>(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), b1.z, b1.w);
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_addr(act_base, r, c0 + 8 * g)), "r"(o0),
                                          "r"(o1), "r"(o2), "r"(o3) : "memory");
                         }
