@@ -298,30 +298,40 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D + forward + decode + D2H inside) ----
     e2e = None
+    e2e_u8 = None
     if not args.no_e2e:
+        def time_host_path(x_np, bytes_per_elem):
+            for _ in range(2):
+                model.detect(x_np, image_size=img_size)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                rec = model.detect(x_np, image_size=img_size)     # vitdet_predict_host[_u8]: synchronous, returns numpy records
+                if world > 1:
+                    parallel.all_gather_records(torch.from_numpy(parallel.pack_records(rec)).to(dev))
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            tt = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return {"value": world * B * args.steps / float(tt.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": int(world * B * np.prod(cfg.input_shape) * bytes_per_elem),
+                    "d2h_bytes_per_step": int(world * B * (S * 24 + rec_bytes)),
+                    "host_affinity": (f"{len(numa_cpus)} cpus local to the GPU" if numa_cpus else "unbound")}
+
         x_host = torch.empty((B, *cfg.input_shape), dtype=torch.float32, pin_memory=True)
         x_host.copy_(x_dev)
-        x_np = x_host.numpy()
-        for _ in range(2):
-            model.detect(x_np, image_size=img_size)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            rec = model.detect(x_np, image_size=img_size)     # vitdet_predict_host: synchronous, returns numpy records
-            if world > 1:
-                parallel.all_gather_records(torch.from_numpy(parallel.pack_records(rec)).to(dev))
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        tt = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * args.steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(world * B * np.prod(cfg.input_shape) * 4),
-               "d2h_bytes_per_step": int(world * B * (S * 24 + rec_bytes)),
-               "host_affinity": (f"{len(numa_cpus)} cpus local to the GPU" if numa_cpus else "unbound")}
+        e2e = time_host_path(x_host.numpy(), 4)
+        # the same call fed with the uint8 pixels the reference's input pipeline starts from
+        # (vision_transformer_utilities.py:446-447: x / 127.5 - 1, here inside the patch kernel); extra, not the headline
+        u_host = torch.empty((B, *cfg.input_shape), dtype=torch.uint8, pin_memory=True)
+        u_host.copy_(((x_dev + 1) * 127.5).round().clamp(0, 255).to(torch.uint8))
+        e2e_u8 = time_host_path(u_host.numpy(), 1)
+        e2e_u8["input"] = "uint8 NHWC pixels, normalised on the device"
+        del x_host, u_host
 
     # ---- roofline of the dominant kernel (the 3584 -> 1792 MLP GEMM in the default config) ----
     roofline = None
@@ -376,7 +386,7 @@ def run_ours(args):
                        "global_batch": B * world, "tokens": cfg.tokens, "flop_per_image": fpi,
                        "l2_policy": "inputs and activations (>= 283 MB per step) exceed the 126 MB L2; no flush between steps"},
             "model_tflops": value * fpi / 1e12,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_uint8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         if breakdown:
             line["breakdown"] = breakdown

@@ -190,6 +190,20 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
                         const vitdet_decode_params* params, float* logits_host,
                         const vitdet_detections* out_host, void* stream);
 
+/* ---- uint8 input ("next" row N4, fused with the patch kernel) ----
+ * The reference's input pipeline turns uint8 pixels into the model's float32 input with x / 127.5 - 1
+ * (vision_transformer_utilities.py:446-447).  These two entry points take the uint8 pixels themselves — NHWC
+ * [B, image_h, image_w, 3], already at the model's size — and apply that normalisation inside the patch kernel, so
+ * the float32 image is never materialised and the host->device copy is a quarter of the float32 one.  Results are
+ * bit-identical to vitdet_forward / vitdet_predict_host on the normalised float32 images. */
+/* DEVICE pointers; logits_dev may be NULL when (params, out) are given and vice versa. */
+int vitdet_forward_u8(vitdet_handle* h, const uint8_t* images_dev, int B, float* logits_dev, int mode,
+                      const vitdet_decode_params* params, const vitdet_detections* out, void* stream);
+/* HOST pointers; same contract as vitdet_predict_host. */
+int vitdet_predict_host_u8(vitdet_handle* h, const uint8_t* images_host, int B, int mode,
+                           const vitdet_decode_params* params, float* logits_host,
+                           const vitdet_detections* out_host, void* stream);
+
 /* ---- evaluation metric ("next" row N2): MeanAveragePrecision of the reference (det.py:1268-2060) ----
  * The COCO-style AP of the reference: mean over the IoU thresholds tf.linspace(0.5, 0.95, 10) of the mean, over the
  * classes seen so far, of the class AP computed from the latest `latest_related_images` related images per class

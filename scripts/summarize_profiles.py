@@ -105,7 +105,7 @@ if __name__ == "__main__":
     traffic(tag)
     for rep in sorted(x[:-8] for x in os.listdir(OUT) if x.endswith(".ncu-rep")):
         full(tag, rep)
-    for name in ("bench_n1.json", "pytest_gpu.log"):
+    for name in ("bench_n1.json", "bench_metric.json", "pytest_gpu.log"):
         if os.path.exists(os.path.join(OUT, name)):
             shutil.copy(os.path.join(OUT, name), os.path.join(PROF, f"{tag}_{name}"))
     print(sorted(os.listdir(PROF)))

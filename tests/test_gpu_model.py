@@ -328,3 +328,24 @@ def test_full_size_batch_properties():
     assert np.array_equal(rec.class_id.cpu().numpy(), cid) and np.array_equal(rec.keep.cpu().numpy().astype(bool), keep)
     assert np.array_equal(rec.corners.cpu().numpy(), oracle.corners(dec, cfg.input_shape[:2]))
     m.close()
+
+
+def test_uint8_pixels_are_normalised_on_the_device_bit_exactly():
+    """uint8 input ("next" row N4 fused into the patch kernel): x / 127.5 - 1 (utilities.py:446-447) happens inside
+    patchify, so predict(uint8) must equal predict(normalised float32) bit for bit, on the host and the device path."""
+    import torch
+    cfg = tiny_config()
+    rng = np.random.default_rng(7)
+    u8 = rng.integers(0, 256, size=(5, *cfg.input_shape), dtype=np.uint8)
+    u8[0, :3] = 0
+    u8[1, -3:] = 255
+    f32 = u8.astype(np.float32) / np.float32(127.5) - np.float32(1)
+    for mode in ("fp32", "bf16"):
+        model = build_model(cfg, vd.random_weights(cfg, seed=3, spread=True), mode)
+        ref = model.predict(f32)
+        assert np.array_equal(model.predict(u8), ref)
+        assert np.array_equal(model(torch.from_numpy(u8).cuda()).cpu().numpy(), ref)
+        a, b = model.detect(u8), model.detect(f32)
+        assert np.array_equal(a.keep, b.keep) and np.array_equal(a.class_id, b.class_id) and np.array_equal(a.decoded, b.decoded)
+        d = model.detect(torch.from_numpy(u8).cuda())
+        assert np.array_equal(d.decoded.cpu().numpy(), b.decoded) and np.array_equal(d.corners.cpu().numpy(), b.corners)

@@ -88,6 +88,8 @@ SYMBOLS = {
     "vitdet_resize_with_pad_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "vitdet_iou": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "vitdet_iou_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "vitdet_forward_u8": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.POINTER(DecodeParams), C.POINTER(Detections), _P]),
+    "vitdet_predict_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(DecodeParams), _P, C.POINTER(Detections), _P]),
     "vitdet_map_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vitdet_map_destroy": (None, [_P]),
     "vitdet_map_reset": (C.c_int, [_P, _P]),

@@ -117,6 +117,11 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float a0, float a1, float b0
         f2_unpack(mish2_fast(f2_add(f2_pack(a0, a1), f2_pack(b0, b1))), y0, y1);
         return pack_bf16x2(y0, y1);
     }
+    if (ACT == ACT_NONE) {
+        float y0, y1;
+        f2_unpack(f2_add(f2_pack(a0, a1), f2_pack(b0, b1)), y0, y1);
+        return pack_bf16x2(y0, y1);
+    }
     return pack_bf16x2(apply_act<ACT, false>(a0 + b0), apply_act<ACT, false>(a1 + b1));
 }
 

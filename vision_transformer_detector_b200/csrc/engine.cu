@@ -688,9 +688,10 @@ struct ForwardOpts {
     int lead_chunks[2] = {0, 0};      // sizes of the first two encoder chunks (0 = use the regular chunk)
     const cudaEvent_t* ready = nullptr;
     int ready_gran = 0;
+    int in_u8 = 0;                    // images are uint8 pixels; the patch kernel normalises them (x / 127.5 - 1)
 };
 
-static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, float* logits,
+static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, float* logits,
                         const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st,
                         const ForwardOpts& opts = ForwardOpts()) {
     if (!h || !images || B <= 0) return fail(VITDET_E_INVALID, "forward: bad arguments");
@@ -723,9 +724,9 @@ static int forward_impl(vitdet_handle* h, const float* images, int B, int mode, 
             ep = &h->enc_plans[bc];
             if (!ep->valid) RC_TRY(build_enc_plans(h, bc, ep));
         }
-        const float* img = images + static_cast<size_t>(c0) * c.image_h * c.image_w * 3;
+        const char* img = static_cast<const char*>(images) + static_cast<size_t>(c0) * c.image_h * c.image_w * 3 * (opts.in_u8 ? 1 : 4);
         { ProfScope ps(h, PC_PATCHIFY, st);
-        CU_TRY(patchify_launch(img, bc, c.image_h, c.image_w, c.patch_size, h->patch.p, bf ? m.Pld : round_up(h->PK, 4), h->RP, out_f32_act, st)); }
+        CU_TRY(patchify_launch(img, opts.in_u8, bc, c.image_h, c.image_w, c.patch_size, h->patch.p, bf ? m.Pld : round_up(h->PK, 4), h->RP, out_f32_act, st)); }
         if (bf) {
             ProfScope ps(h, PC_PROJ, st);
             RC_TRY(launch_tc(ep->proj, x, nullptr, st));
@@ -1000,6 +1001,15 @@ int vitdet_forward(vitdet_handle* h, const float* images_dev, int B, float* logi
     return forward_impl(h, images_dev, B, mode, logits_dev, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int vitdet_forward_u8(vitdet_handle* h, const uint8_t* images_dev, int B, float* logits_dev, int mode, const vitdet_decode_params* params,
+                      const vitdet_detections* out, void* stream) {
+    if (!logits_dev && !(params && out)) return fail(VITDET_E_INVALID, "forward_u8: neither logits_dev nor (params, out) given");
+    if ((params == nullptr) != (out == nullptr)) return fail(VITDET_E_INVALID, "forward_u8: params and out go together");
+    ForwardOpts opts;
+    opts.in_u8 = 1;
+    return forward_impl(h, images_dev, B, mode, logits_dev, params, out, static_cast<cudaStream_t>(stream), opts);
+}
+
 int vitdet_forward_decode(vitdet_handle* h, const float* images_dev, int B, int mode, const vitdet_decode_params* params,
                           float* logits_dev, const vitdet_detections* out, void* stream) {
     if (!params || !out) return fail(VITDET_E_INVALID, "forward_decode: null params / out");
@@ -1088,11 +1098,13 @@ int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_para
     return 0;
 }
 
-int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int mode, const vitdet_decode_params* params,
-                        float* logits_host, const vitdet_detections* out_host, void* stream) {
+}  // extern "C"
+
+static int predict_host_impl(vitdet_handle* h, const void* images_host, int in_u8, int B, int mode, const vitdet_decode_params* params,
+                             float* logits_host, const vitdet_detections* out_host, void* stream) {
     if (!h || !images_host || B <= 0 || !params) return fail(VITDET_E_INVALID, "predict_host: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t in_bytes = static_cast<size_t>(B) * h->cfg.image_h * h->cfg.image_w * 3 * 4;
+    const size_t in_bytes = static_cast<size_t>(B) * h->cfg.image_h * h->cfg.image_w * 3 * (in_u8 ? 1 : 4);
     const size_t R = static_cast<size_t>(B) * h->S;
     // output record block: logits 24 | decoded 24 | class_id 4 | class_conf 4 | corners 16 | keep 1  bytes per row
     const size_t o_logits = 0, o_dec = a256(R * 24), o_id = o_dec + a256(R * 24), o_cc = o_id + a256(R * 4),
@@ -1119,6 +1131,7 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     // through the handle's pinned buffer first (what a pageable cudaMemcpyAsync would do, serially).
     // VITDET_E2E_LEAD="g,a,b" overrides the copy granularity and the two lead chunk sizes (tuning experiments)
     int kGran = 4, lead0 = 4, lead1 = 12;
+    if (in_u8) { kGran = 16; lead0 = 16; lead1 = 0; }       // a quarter of the bytes per image: same 0.3 ms lead-in with 16 images
     if (const char* e = getenv("VITDET_E2E_LEAD")) sscanf(e, "%d,%d,%d", &kGran, &lead0, &lead1);
     if (kGran < 1) kGran = 8;
     const int n_sub = (B + kGran - 1) / kGran;
@@ -1155,6 +1168,7 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     else if (B > lead0) opts.lead_chunks[0] = lead0;
     opts.ready = h->copy_events.data();
     opts.ready_gran = kGran;
+    opts.in_u8 = in_u8;
     char* dbase = h->dev_out.as<char>();
     vitdet_detections d;
     d.decoded = reinterpret_cast<float*>(dbase + o_dec);
@@ -1162,7 +1176,7 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
     d.class_conf = reinterpret_cast<float*>(dbase + o_cc);
     d.corners = reinterpret_cast<int32_t*>(dbase + o_cor);
     d.keep = reinterpret_cast<uint8_t*>(dbase + o_keep);
-    RC_TRY(forward_impl(h, h->dev_in.as<float>(), B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st, opts));
+    RC_TRY(forward_impl(h, h->dev_in.p, B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st, opts));
     CU_TRY(cudaMemcpyAsync(h->pin_out, dbase, out_bytes, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     const char* pb = static_cast<const char*>(h->pin_out);
@@ -1175,6 +1189,18 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
         if (out_host->keep) memcpy(out_host->keep, pb + o_keep, R);
     }
     return 0;
+}
+
+extern "C" {
+
+int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int mode, const vitdet_decode_params* params,
+                        float* logits_host, const vitdet_detections* out_host, void* stream) {
+    return predict_host_impl(h, images_host, 0, B, mode, params, logits_host, out_host, stream);
+}
+
+int vitdet_predict_host_u8(vitdet_handle* h, const uint8_t* images_host, int B, int mode, const vitdet_decode_params* params,
+                           float* logits_host, const vitdet_detections* out_host, void* stream) {
+    return predict_host_impl(h, images_host, 1, B, mode, params, logits_host, out_host, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1277,7 +1303,7 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
 
 int vitdet_op_patchify(const float* images, int B, int H, int W, int p, float* patches, void* stream) {
     if (!images || !patches || B <= 0 || H <= 0 || W <= 0 || p <= 0) return fail(VITDET_E_INVALID, "op_patchify: bad arguments");
-    CU_TRY(patchify_launch(images, B, H, W, p, patches, 3 * p * p, 3 * p, 1, static_cast<cudaStream_t>(stream)));
+    CU_TRY(patchify_launch(images, 0, B, H, W, p, patches, 3 * p * p, 3 * p, 1, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -120,8 +120,8 @@ cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 // tf.image.extract_patches(sizes=strides=p, padding='SAME') + Reshape (det.py:195-197, 279-280).
 // images f32 NHWC [B,H,W,3] -> patches [B*gh*gw, ldp]: element r*rp + c*3 + ch (rp >= 3p = run pitch of one
 // patch row; rp = 3p is the reference's dense vector), zero padded.
-cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int rp,
-                            int out_f32, cudaStream_t stream);
+cudaError_t patchify_launch(const void* images, int in_u8 /*1: uint8 pixels, normalised x/127.5-1 on the fly*/, int B, int H, int W, int p,
+                            void* patches, int ldp, int rp, int out_f32, cudaStream_t stream);
 
 // keras LayerNormalization(axis=-1), eps=1e-3, biased variance (det.py:353-357, 375-379).
 cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D,

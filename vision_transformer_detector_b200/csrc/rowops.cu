@@ -54,9 +54,15 @@ template <> struct Vec4Store<__nv_bfloat16> {
     }
 };
 
-template <typename T, bool VEC>
+// Pixel fetch of the patch kernel: float32 images are already normalised; uint8 images are normalised on the fly,
+// /127.5 then -1 exactly as the reference's input pipeline does (vision_transformer_utilities.py:446-447), so the
+// float32 image never exists in HBM and the host->device copy is a quarter of the size.
+__device__ __forceinline__ float ld_pixel(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_pixel(const uint8_t* p) { return __fsub_rn(__fdiv_rn(static_cast<float>(__ldg(p)), 127.5f), 1.f); }
+
+template <typename T, bool VEC, typename IN>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ img, int H, int W, int p, int gh, int gw, int pad_top,
+patchify_kernel(const IN* __restrict__ img, int H, int W, int p, int gh, int gw, int pad_top,
                 int pad_left, T* __restrict__ out, int ldp, int rp) {
     pdl_launch_dependents();
     pdl_wait();
@@ -76,7 +82,7 @@ patchify_kernel(const float* __restrict__ img, int H, int W, int p, int gh, int 
     for (int r = 0; r < p; ++r) {
         const int y = py * p + r - pad_top;
         const bool y_ok = (y >= 0) && (y < H);
-        const float* src = img + (static_cast<size_t>(b) * H + (y_ok ? y : 0)) * W3 - 3 * pad_left;
+        const IN* src = img + (static_cast<size_t>(b) * H + (y_ok ? y : 0)) * W3 - 3 * pad_left;
         for (int px = warp * runs_per_warp + sub; px < gw; px += 8 * runs_per_warp) {
             T* dst = out + (tok0 + px) * ldp + r * rp;
             const int x0 = px * run;                       // index into the padded row; source index = x0 + w - 3*pad_left
@@ -87,12 +93,12 @@ patchify_kernel(const float* __restrict__ img, int H, int W, int p, int gh, int 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int x3 = x0 + w + j - 3 * pad_left;
-                        v[j] = (y_ok && w + j < run && x3 >= 0 && x3 < W3) ? __ldg(src + x0 + w + j) : 0.f;
+                        v[j] = (y_ok && w + j < run && x3 >= 0 && x3 < W3) ? ld_pixel(src + x0 + w + j) : 0.f;
                     }
                     Vec4Store<T>::st(dst + w, v[0], v[1], v[2], v[3]);
                 } else {
                     const int x3 = x0 + q - 3 * pad_left;
-                    OutT<T>::st(dst + q, (y_ok && q < run && x3 >= 0 && x3 < W3) ? __ldg(src + x0 + q) : 0.f);
+                    OutT<T>::st(dst + q, (y_ok && q < run && x3 >= 0 && x3 < W3) ? ld_pixel(src + x0 + q) : 0.f);
                 }
             }
         }
@@ -377,8 +383,9 @@ cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b,
 
 }  // namespace
 
-cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, void* patches, int ldp, int rp, int out_f32,
-                            cudaStream_t stream) {
+template <typename IN>
+static cudaError_t patchify_launch_t(const IN* images, int B, int H, int W, int p, void* patches, int ldp, int rp, int out_f32,
+                                     cudaStream_t stream) {
     const int gh = (H + p - 1) / p, gw = (W + p - 1) / p;
     const int pad_top = (gh * p - H) / 2, pad_left = (gw * p - W) / 2;
     if (rp < 3 * p || ldp < rp * p) return cudaErrorInvalidValue;
@@ -388,12 +395,18 @@ cudaError_t patchify_launch(const float* images, int B, int H, int W, int p, voi
     const bool vec = (rp % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
     if (out_f32) {
         float* o = static_cast<float*>(patches);
-        if (vec) return launch_kernel(patchify_kernel<float, true>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
-        return launch_kernel(patchify_kernel<float, false>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+        if (vec) return launch_kernel(patchify_kernel<float, true, IN>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+        return launch_kernel(patchify_kernel<float, false, IN>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
     }
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(patches);
-    if (vec) return launch_kernel(patchify_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
-    return launch_kernel(patchify_kernel<__nv_bfloat16, false>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+    if (vec) return launch_kernel(patchify_kernel<__nv_bfloat16, true, IN>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+    return launch_kernel(patchify_kernel<__nv_bfloat16, false, IN>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
+}
+
+cudaError_t patchify_launch(const void* images, int in_u8, int B, int H, int W, int p, void* patches, int ldp, int rp, int out_f32,
+                            cudaStream_t stream) {
+    if (in_u8) return patchify_launch_t(static_cast<const uint8_t*>(images), B, H, W, p, patches, ldp, rp, out_f32, stream);
+    return patchify_launch_t(static_cast<const float*>(images), B, H, W, p, patches, ldp, rp, out_f32, stream);
 }
 
 cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D, float eps,

@@ -255,6 +255,11 @@ def _decode_params(objectness_threshold, classification_threshold, strict, image
     return p
 
 
+def _is_uint8(x) -> bool:
+    """uint8 pixels (numpy or torch): normalised x / 127.5 - 1 inside the patch kernel (utilities.py:446-447)."""
+    return str(getattr(x, "dtype", "")).endswith("uint8")
+
+
 def _is_torch_cuda(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
 
@@ -663,21 +668,26 @@ class VisionTransformerDetector:
             image_size = self.config.input_shape[:2]
         params = _decode_params(objectness_threshold, classification_threshold, strict, image_size)
         mode = self._mode(compute_mode)
+        u8 = _is_uint8(x)
         if _is_torch_cuda(x):
             import torch
-            xi = x.to(torch.float32).contiguous()
+            xi = x.contiguous() if u8 else x.to(torch.float32).contiguous()
             with torch.cuda.device(xi.device):
                 logits, dec, cid, cc, keep, cor = _alloc_records_torch(B, S, xi.device)
                 st = _records_struct(dec, cid, cc, keep, cor)
-                _capi.check(self._lib.vitdet_forward_decode(self._h, C.c_void_p(xi.data_ptr()), B, mode, C.byref(params),
-                                                            C.c_void_p(logits.data_ptr()), C.byref(st),
-                                                            _torch_stream_ptr(xi.device)))
+                if u8:
+                    _capi.check(self._lib.vitdet_forward_u8(self._h, C.c_void_p(xi.data_ptr()), B, C.c_void_p(logits.data_ptr()), mode,
+                                                            C.byref(params), C.byref(st), _torch_stream_ptr(xi.device)))
+                else:
+                    _capi.check(self._lib.vitdet_forward_decode(self._h, C.c_void_p(xi.data_ptr()), B, mode, C.byref(params),
+                                                                C.c_void_p(logits.data_ptr()), C.byref(st),
+                                                                _torch_stream_ptr(xi.device)))
             return DetectionRecords(logits, dec, cid, cc, keep, cor)
-        xi = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         logits, dec, cid, cc, keep, cor = _alloc_records_np(B, S)
         st = _records_struct(dec, cid, cc, keep, cor)
-        _capi.check(self._lib.vitdet_predict_host(self._h, _capi.np_ptr(xi), B, mode, C.byref(params), _capi.np_ptr(logits),
-                                                  C.byref(st), None))
+        fn = self._lib.vitdet_predict_host_u8 if u8 else self._lib.vitdet_predict_host
+        _capi.check(fn(self._h, _capi.np_ptr(xi), B, mode, C.byref(params), _capi.np_ptr(logits), C.byref(st), None))
         return DetectionRecords(logits, dec, cid, cc, keep, cor)
 
     def predict(self, x, batch_size=None, verbose="auto", steps=None, callbacks=None, **kwargs):
@@ -687,11 +697,12 @@ class VisionTransformerDetector:
         if _is_torch_cuda(x):
             return self(x).cpu().numpy()
         B = self._check_images(np.shape(x))
-        xi = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        u8 = _is_uint8(x)      # raw pixels: normalised on the device, a quarter of the float32 copy
+        xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         logits = np.empty((B, Constants.MAX_DETECT_OBJECTS_QUANTITY.value, 6), np.float32)
         params = _decode_params(None, None, True, self.config.input_shape[:2])
-        _capi.check(self._lib.vitdet_predict_host(self._h, _capi.np_ptr(xi), B, self._mode(), C.byref(params),
-                                                  _capi.np_ptr(logits), None, None))
+        fn = self._lib.vitdet_predict_host_u8 if u8 else self._lib.vitdet_predict_host
+        _capi.check(fn(self._h, _capi.np_ptr(xi), B, self._mode(), C.byref(params), _capi.np_ptr(logits), None, None))
         return logits
 
     def __call__(self, x, training=False, compute_mode: str | None = None):
@@ -703,11 +714,16 @@ class VisionTransformerDetector:
             return self.predict(x)
         import torch
         B = self._check_images(x.shape)
-        xi = x.to(torch.float32).contiguous()
+        u8 = _is_uint8(x)
+        xi = x.contiguous() if u8 else x.to(torch.float32).contiguous()
         with torch.cuda.device(xi.device):
             logits = torch.empty((B, Constants.MAX_DETECT_OBJECTS_QUANTITY.value, 6), dtype=torch.float32, device=xi.device)
-            _capi.check(self._lib.vitdet_forward(self._h, C.c_void_p(xi.data_ptr()), B, C.c_void_p(logits.data_ptr()),
-                                                 self._mode(compute_mode), _torch_stream_ptr(xi.device)))
+            if u8:
+                _capi.check(self._lib.vitdet_forward_u8(self._h, C.c_void_p(xi.data_ptr()), B, C.c_void_p(logits.data_ptr()),
+                                                        self._mode(compute_mode), None, None, _torch_stream_ptr(xi.device)))
+            else:
+                _capi.check(self._lib.vitdet_forward(self._h, C.c_void_p(xi.data_ptr()), B, C.c_void_p(logits.data_ptr()),
+                                                     self._mode(compute_mode), _torch_stream_ptr(xi.device)))
         return logits
 
 
