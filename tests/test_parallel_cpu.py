@@ -71,3 +71,41 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     whole = parallel.pack_records(_records_from_logits(logits))
     assert gathered.shape == whole.shape == (total * 17, parallel.RECORD_WIDTH)
     assert np.array_equal(gathered, whole)            # rank order == batch order, bit-exact
+
+
+def _metric_worker(rank: int, world: int, port: int, total: int, out_dir: str):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import map_oracle
+    from _util import map_case
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    metric = map_oracle.MeanAveragePrecision()          # stands in for the GPU metric: same update_state signature
+    for step in range(2):
+        y_true, y_pred = map_case(60 + step, total, 17)                       # same on every rank
+        lo, hi = parallel.shard_bounds(total, world, rank)
+        parallel.update_metric_sharded(metric, torch.from_numpy(y_true[lo:hi]), torch.from_numpy(y_pred[lo:hi]),
+                                       use_transform_predictions=False)
+    np.save(os.path.join(out_dir, f"state_{rank}.npy"), metric.latest_positive_bboxes)
+    np.save(os.path.join(out_dir, f"ap_{rank}.npy"), np.array([metric.result()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_metric_equals_single_process(tmp_path):
+    """The metric depends on the ORDER of the images (latest related images per class): sharded evaluation must gather
+    the shards in rank order so that every rank ends with the single-process state."""
+    import map_oracle
+    from _util import map_case
+    total, world = 12, 2
+    port = _free_port()
+    mp.spawn(_metric_worker, args=(world, port, total, str(tmp_path)), nprocs=world, join=True)
+    ref = map_oracle.MeanAveragePrecision()
+    for step in range(2):
+        y_true, y_pred = map_case(60 + step, total, 17)
+        ref.update_state(y_true, y_pred, use_transform_predictions=False)
+    for rank in range(world):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"state_{rank}.npy")), ref.latest_positive_bboxes)
+        assert np.load(os.path.join(str(tmp_path), f"ap_{rank}.npy"))[0] == ref.result()

@@ -51,3 +51,27 @@ def all_gather_records(packed):
     out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out, packed.contiguous())
     return out
+
+
+def update_metric_sharded(metric, y_true_local, y_pred_local, use_transform_predictions: bool = True) -> None:
+    """Evaluation with the batch sharded over ranks: the metric keeps the LATEST related images per class in dataset
+    order (det.py:1427, 1852-1857), so the shards are all-gathered in rank order (= the contiguous shard_bounds order)
+    and every rank applies the same update to its own replica of the state; `metric.result()` is then identical on
+    all ranks and to a single-process run over the whole batch.  Shards must be equally sized (pad the last batch).
+    y_*_local: (B_local, slots, 6) torch tensors on the rank's device (CUDA with NCCL, CPU with gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        metric.update_state(y_true_local, y_pred_local, use_transform_predictions=use_transform_predictions)
+        return
+    world = dist.get_world_size()
+    both = torch.stack([torch.as_tensor(y_true_local, dtype=torch.float32),
+                        torch.as_tensor(y_pred_local, dtype=torch.float32).to(y_true_local.device)]).contiguous()   # (2, B_local, S, 6)
+    flat = torch.empty((world * 2, *both.shape[1:]), dtype=both.dtype, device=both.device)
+    dist.all_gather_into_tensor(flat, both)
+    out = flat.view(world, *both.shape)
+    y_true = out[:, 0].reshape(-1, *both.shape[2:])          # rank-major = global image order
+    y_pred = out[:, 1].reshape(-1, *both.shape[2:])
+    if not y_true.is_cuda:                                   # gloo / CPU tensors: hand numpy to the metric
+        y_true, y_pred = y_true.numpy(), y_pred.numpy()
+    metric.update_state(y_true, y_pred, use_transform_predictions=use_transform_predictions)
