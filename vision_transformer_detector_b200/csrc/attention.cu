@@ -78,11 +78,11 @@ attn_f32_kernel(const float* __restrict__ qkv, int ldq, float* __restrict__ ctx,
 
 }  // namespace
 
-// Tensor map over the fused qkv matrix [B*T, 3*H*64] (bf16): boxes of 64 rows x 64 columns, 128B swizzle; the
-// tcgen05 kernel loads Q, K and V tiles of one head through it.
+// Tensor map over the fused qkv matrix [B*T, 3*H*hp] (bf16): boxes of 64 rows x 64 columns, 128B swizzle, placed at
+// column head * hp; hp = key_dim rounded up to 8.  For hp < 64 a box also carries the first columns of the next head
+// (zeros past the end of the matrix); the kernel neutralises them (attention_tc.cu).
 int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d) {
-    constexpr int kHP = 64;
-    if (d.hp != kHP || d.d <= 0 || d.d > kHP) return -20;       // key_dim > 64 not supported in this build
+    if (d.d <= 0 || d.hp < d.d || d.hp > 64 || (d.hp % 8)) return -20;       // key_dim > 64 not supported in this build
     if ((d.ldq % 8) || (d.ldo % 8) || d.ldq < 3 * d.H * d.hp || d.ldo < d.H * d.hp) return -21;
     if ((reinterpret_cast<uintptr_t>(d.qkv) & 15) || (reinterpret_cast<uintptr_t>(d.ctx) & 15)) return -22;
     plan->desc = d;

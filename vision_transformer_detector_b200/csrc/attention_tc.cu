@@ -48,6 +48,7 @@ struct AttnTcArgs {
     __nv_bfloat16* ctx;
     int ldo;
     int T, H;
+    int hp;              // elements per head in qkv / ctx (key_dim rounded up to 8)
     int k16;             // ceil(d / 16): K steps of the QK^T product
     float scale_log2;    // log2(e) / sqrt(key_dim)
 };
@@ -204,8 +205,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQKV);
             mbar_arrive_expect_tx(bar_q, kQBytes);
-            tma_load_2d(sQ, &tmQKV, bar_q, h * kHP, row_base + q0);
-            tma_load_2d(sQ + kBoxBytes, &tmQKV, bar_q, h * kHP, row_base + q0 + 64);
+            tma_load_2d(sQ, &tmQKV, bar_q, h * p.hp, row_base + q0);
+            tma_load_2d(sQ + kBoxBytes, &tmQKV, bar_q, h * p.hp, row_base + q0 + 64);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < nkv; ++j) {
@@ -213,10 +214,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                 mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kTileBytes);
                 const uint32_t dK = sKV + stage * 2 * kTileBytes;
                 const int r = row_base + j * kKV;
-                tma_load_2d(dK, &tmQKV, bar_full + 8 * stage, (p.H + h) * kHP, r);
-                tma_load_2d(dK + kBoxBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * kHP, r + 64);
-                tma_load_2d(dK + kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * kHP, r);
-                tma_load_2d(dK + kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * kHP, r + 64);
+                tma_load_2d(dK, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp, r);
+                tma_load_2d(dK + kBoxBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp, r + 64);
+                tma_load_2d(dK + kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp, r);
+                tma_load_2d(dK + kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp, r + 64);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -232,6 +233,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         const uint64_t dkv0 = umma_desc_sw128_kmajor(sKV);
         constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4, kVOff = kTileBytes >> 4;     // descriptor address units (16 B)
         mbar_wait(bar_q, 0);
+        // Heads are stored hp (< 64) columns apart, so the 64-column TMA boxes also carry the first columns of the
+        // next head.  In QK^T only the columns below 16 * k16 take part: clearing Q's columns [hp, 16 * k16) once makes
+        // their products vanish whatever K holds there; V's extra columns only produce columns of O that are never
+        // stored.  16-byte chunk c of row r sits at chunk c ^ (r & 7) of the 128-byte swizzled row.
+        if (p.hp < 16 * p.k16) {
+            const int c_lo = p.hp >> 3, c_hi = 2 * p.k16;
+            for (int r = lane; r < kQ; r += 32)
+                for (int c = c_lo; c < c_hi; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + r * 128 + ((c ^ (r & 7)) << 4)), "r"(0u) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+        }
         int stage = 0;
         uint32_t phase = 0;
         for (int j = 0; j <= nkv; ++j) {
@@ -303,7 +316,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         tc_fence_after();
         const int q = q0 + quad * 32 + lane;
         const float inv = 1.f / l;
-        __nv_bfloat16* orow = p.ctx + static_cast<size_t>(row_base + (q < p.T ? q : 0)) * p.ldo + h * kHP;
+        __nv_bfloat16* orow = p.ctx + static_cast<size_t>(row_base + (q < p.T ? q : 0)) * p.ldo + h * p.hp;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -312,6 +325,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             if (q < p.T) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
+                    if (32 * c + 8 * g >= p.hp) break;          // the head holds hp columns; O's further columns are zero
                     uint4 w;
                     w.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
                     w.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
@@ -340,6 +354,7 @@ cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream) {
     a.ldo = d.ldo;
     a.T = d.T;
     a.H = d.H;
+    a.hp = d.hp;
     a.k16 = (d.d + 15) / 16;
     a.scale_log2 = d.scale * 1.4426950408889634f;
     const size_t smem = static_cast<size_t>(kQBytes) + static_cast<size_t>(kStages) * 2 * kTileBytes;

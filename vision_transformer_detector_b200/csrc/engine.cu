@@ -50,7 +50,10 @@ int fail(int code, const char* fmt, ...) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-constexpr int kHeadPitch = 64;   // elements per head slot in qkv / ctx (one 128-byte swizzle row of bf16)
+constexpr int kMaxKeyDim = 64;    // one 128-byte swizzle row of bf16 per head in shared memory
+// Elements per head in the qkv / ctx matrices: key_dim rounded up to 8 (16-byte rows for TMA and vector stores).  The
+// attention kernel's tensor map zero-fills columns hp..63 of every head tile, so HBM carries no 64-wide pad.
+static inline int head_pitch(int key_dim) { return (key_dim + 7) / 8 * 8; }
 
 static cudaError_t attn_launch(const AttnPlan& plan, cudaStream_t st) { return attn_tc_launch(plan, st); }
 
@@ -192,6 +195,7 @@ struct vitdet_handle {
     int device = 0;
     int num_sms = 148;
     int gh = 0, gw = 0, T = 0, P = 0, D = 0, H = 0, d = 0, S = 0;
+    int hp = 0;                                // head_pitch(d)
     int RP = 0, PK = 0;                 // run pitch of one patch row (round_up(3p, 4)) and padded patch vector p * RP
     int act = ACT_MISH;
     int chunk = 64;
@@ -300,7 +304,7 @@ static int add_vec_slot(vitdet_handle* h, const std::string& name, DevBuf* buf, 
 
 static int build_weight_table(vitdet_handle* h) {
     const vitdet_config& c = h->cfg;
-    const int D = h->D, H = h->H, d = h->d, T = h->T, P = h->P, S = h->S, hp = kHeadPitch;
+    const int D = h->D, H = h->H, d = h->d, T = h->T, P = h->P, S = h->S, hp = h->hp;
 
     // transformer_preprocessor: Dense 'linear_projection' (det.py:297) then PositionEncoding's
     // Embedding(T, 1) 'position_encoding/position_embedding' (det.py:148-151, 291-293).
@@ -472,8 +476,8 @@ static Dims dims_for(const vitdet_handle* h, int mode) {
     m.D4 = round_up(h->D, 4);
     m.D8 = round_up(h->D, 8);
     m.Pld = round_up(h->PK, 8);
-    m.w_qkv = 3 * h->H * kHeadPitch;
-    m.w_ctx = h->H * kHeadPitch;
+    m.w_qkv = 3 * h->H * h->hp;
+    m.w_ctx = h->H * h->hp;
     // MLP ping-pong: layer j writes buffer j & 1; widest even / odd layer outputs.
     m.w_u0 = 8; m.w_u1 = 8;
     for (int j = 0; j + 1 < c.mlp_quantities; ++j) {
@@ -555,7 +559,7 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
         RC_TRY(plan_dense(h, qc, &ep->qkv[i]));
         AttnDesc ad;
         ad.qkv = h->qkv.p; ad.ldq = m.w_qkv; ad.ctx = h->ctx.p; ad.ldo = m.w_ctx;
-        ad.B = bc; ad.T = h->T; ad.H = h->H; ad.d = h->d; ad.hp = kHeadPitch;
+        ad.B = bc; ad.T = h->T; ad.H = h->H; ad.d = h->d; ad.hp = h->hp;
         ad.scale = 1.f / sqrtf(static_cast<float>(h->d));
         int rc = attn_bf16_make_plan(&ep->attn[i], ad);
         if (rc) return fail(VITDET_E_INVALID, "attn_bf16_make_plan failed: %d", rc);
@@ -749,7 +753,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
                 { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_simt(qc, st)); }
                 AttnDesc ad;
                 ad.qkv = h->qkv.p; ad.ldq = m.w_qkv; ad.ctx = h->ctx.p; ad.ldo = m.w_ctx;
-                ad.B = bc; ad.T = T; ad.H = h->H; ad.d = h->d; ad.hp = kHeadPitch;
+                ad.B = bc; ad.T = T; ad.H = h->H; ad.d = h->d; ad.hp = h->hp;
                 ad.scale = 1.f / sqrtf(static_cast<float>(h->d));
                 { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_f32_launch(ad, st)); }
                 DenseCall oc{h->ctx.p, m.w_ctx, &b.out, nullptr, 1, x, m.D4, x, m.D4, 1, ACT_NONE, Mc};
@@ -853,7 +857,7 @@ int vitdet_create(const vitdet_config* cfg, vitdet_handle** out) {
         c.key_dim <= 0 || c.mlp_quantities <= 0 || c.repeat_times <= 0 || c.head_last_units <= 0 ||
         c.head_dense_layers <= 0 || c.head_block_repeats <= 0 || c.num_slots <= 0 || c.classes <= 1)
         return fail(VITDET_E_INVALID, "vitdet_create: every size in the configuration must be positive");
-    if (c.key_dim > kHeadPitch) return fail(VITDET_E_INVALID, "encoder_key_dim %d > %d is not supported by this build", c.key_dim, kHeadPitch);
+    if (c.key_dim > kMaxKeyDim) return fail(VITDET_E_INVALID, "encoder_key_dim %d > %d is not supported by this build", c.key_dim, kMaxKeyDim);
     if (c.embedding_dim > 2048) return fail(VITDET_E_INVALID, "embedding_dim %d > 2048 is not supported by this build", c.embedding_dim);
     if (c.mlp_quantities > 20 || c.head_dense_layers > 20) return fail(VITDET_E_INVALID, "pyramid depth out of range");
 
@@ -879,6 +883,7 @@ int vitdet_create(const vitdet_config* cfg, vitdet_handle** out) {
     h->RP = round_up(3 * c.patch_size, 4);
     h->PK = c.patch_size * h->RP;
     h->D = c.embedding_dim; h->H = c.num_heads; h->d = c.key_dim; h->S = c.num_slots;
+    h->hp = head_pitch(c.key_dim);
     h->act = c.use_mish ? ACT_MISH : ACT_GELU;
     int rc = build_weight_table(h);
     if (rc) { delete h; return rc; }
@@ -1272,10 +1277,10 @@ int vitdet_op_layernorm(const float* x, const float* gamma, const float* beta, f
 
 int vitdet_op_attention(const float* q, const float* k, const float* v, float* out, int B, int T, int H, int d, int mode,
                         void* stream) {
-    if (!q || !k || !v || !out || B <= 0 || T <= 0 || H <= 0 || d <= 0 || d > kHeadPitch)
-        return fail(VITDET_E_INVALID, "op_attention: bad arguments (key_dim must be <= %d)", kHeadPitch);
+    if (!q || !k || !v || !out || B <= 0 || T <= 0 || H <= 0 || d <= 0 || d > kMaxKeyDim)
+        return fail(VITDET_E_INVALID, "op_attention: bad arguments (key_dim must be <= %d)", kMaxKeyDim);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int hp = kHeadPitch;
+    const int hp = head_pitch(d);
     const long long rows = static_cast<long long>(B) * T;
     const int es = mode == VITDET_MODE_BF16 ? 2 : 4;
     DevBuf qkv, ctx;
