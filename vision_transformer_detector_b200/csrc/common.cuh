@@ -126,6 +126,44 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float a0, float a1, float b0
 }
 
 // ---------------------------------------------------------------------------------------------
+// Coalesced float32 epilogue store for wide outputs.  In the epilogues a thread owns one ROW of the accumulator tile
+// (its TMEM lane), so storing its values directly makes every warp-wide 16-byte access touch 32 different rows — fine for
+// the default 28-wide residual stream (the whole row is one 112-byte segment) but 8x sector over-fetch on the residual
+// read and scattered partial-line writes when the row is hundreds of floats wide (embedding_dim 768).  Here the lane's
+// 16 finished values of a 32-row x 16-column half chunk go through the warp's 2 KB staging tile (64 B per row, 16-byte
+// chunk c of row r at c ^ ((r >> 1) & 3): conflict-free both ways) and come back as 8 rows x 64 contiguous bytes per
+// instruction; the residual is added on that side, read with the same coalesced pattern.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_f32_half_chunk_coalesced(uint32_t s_tile, const float (&y)[16], int lane, int row0, int M,
+                                                               float* __restrict__ out, int ldc, const float* __restrict__ resid,
+                                                               int ldr, int col0) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t dst = s_tile + static_cast<uint32_t>(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(y[4 * g]), "f"(y[4 * g + 1]), "f"(y[4 * g + 2]),
+                     "f"(y[4 * g + 3]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2), ch = lane & 3;
+        const uint32_t src = s_tile + static_cast<uint32_t>(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src) : "memory");
+        const int row = row0 + r;
+        if (row < M) {
+            const int col = col0 + 4 * ch;
+            if (resid != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * ldr + col);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ldc + col) = v;
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (see launch.h)
 // ---------------------------------------------------------------------------------------------
 // Lets the next kernel of the stream start its prologue; call as early as possible.

@@ -205,6 +205,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_wait();
                 const bool full = n0 + c0 + 32 <= p.N;      // block_n is a multiple of 32: chunks are never partial in the tile
                 if (OUT_F32) {
+                    if (full && p.N > 32 && p.ln_out == nullptr) {
+                        // wide float32 output (embedding_dim > 32): finished values of the lane's row, 16 columns at a
+                        // time, through the staging tile to coalesced stores (common.cuh); residual added on that side
+                        const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreTileBytes;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float y16[16];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int c = c0 + 16 * hh + 4 * g;
+                                const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                y16[4 * g + 0] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 0]) + b4.x + pos_v);
+                                y16[4 * g + 1] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 1]) + b4.y + pos_v);
+                                y16[4 * g + 2] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 2]) + b4.z + pos_v);
+                                y16[4 * g + 3] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
+                            }
+                            store_f32_half_chunk_coalesced(s_tile, y16, lane, m0 + quad * 32, p.M, reinterpret_cast<float*>(p.out), p.ldc,
+                                                           p.resid, p.ldr, n0 + c0 + 16 * hh);
+                        }
+                        continue;
+                    }
                     if (!row_ok) continue;
                     float* orow = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc;
                     const float* rrow = p.resid ? p.resid + static_cast<size_t>(row) * p.ldr : nullptr;
