@@ -87,13 +87,33 @@ def test_no_cpu_fallback():
         vd.transform_predictions(np.zeros((1, 17, 6), np.float32))
 
 
+def test_metric_class_mirrors_the_reference_interface():
+    """MeanAveragePrecision (det.py:1268-2060): same constructor default, method names and update_state signature;
+    without a GPU it fails loudly instead of computing on the host."""
+    import inspect
+    import torch
+    m = vd.MeanAveragePrecision
+    sig = inspect.signature(m.update_state)
+    assert list(sig.parameters)[:5] == ["self", "y_true", "y_pred", "sample_weight", "use_transform_predictions"]
+    assert sig.parameters["sample_weight"].default is None and sig.parameters["use_transform_predictions"].default is True
+    assert inspect.signature(m.__init__).parameters["name"].default == "AP"
+    for attr in ("result", "reset_state", "latest_positive_bboxes", "labels_quantity_per_image", "showed_up_classes"):
+        assert hasattr(m, attr)
+    assert (vd.Constants.LATEST_RELATED_IMAGES.value, vd.Constants.BBOXES_PER_IMAGE.value) == (3, 14)     # det.py:32, 37
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.VitdetError) as ei:
+            m()
+        assert ei.value.code == _capi.E_NO_DEVICE
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "vision_transformer_detector_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "vitdet_oracle" not in text and "import oracle" not in text, f"{f} references the oracle"
+                assert "vitdet_oracle" not in text and "import oracle" not in text and "import map_oracle" not in text, \
+                    f"{f} references the oracle"
 
 
 def test_category_names_match_the_reference_table():
