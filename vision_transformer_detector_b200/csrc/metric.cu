@@ -17,7 +17,7 @@
 //     ties, as tf.argsort does) and ten threads walk the sorted list, one per IoU threshold.
 // All float arithmetic the reference does in float32 is done here with the same operations in the same order
 // (__f*_rn intrinsics: no FMA contraction), so state and APs are bit-identical to a float32 restatement
-// (oracle/map_oracle.py).  These kernels move a few hundred KB; they are latency-bound, not roofline material.
+// (what the parity tests compare against).  These kernels move a few hundred KB; they are latency-bound, not roofline material.
 #include <cstdint>
 #include <cstring>
 #include <new>
