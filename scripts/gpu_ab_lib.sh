@@ -1,7 +1,7 @@
 # A/B of two builds inside one box: libvitdet_b200_A.so vs libvitdet_b200_B.so (copied over the product library in turn)
 mkdir -p gpurun_out
 P=vision_transformer_detector_b200
-for rep in 1 2 3; do
+for rep in ${REPS:-1 2 3}; do
 for v in A B; do
   cp $P/libvitdet_b200_$v.so $P/libvitdet_b200.so
   python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e $EXTRA 2>/dev/null | python -c "
