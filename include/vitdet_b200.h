@@ -114,6 +114,24 @@ const char* vitdet_profile_category_name(int category);
 int vitdet_profile_read(vitdet_handle* h, int category, double* total_ms, int64_t* launches, int reset);
 int64_t vitdet_launch_count(vitdet_handle* h, int reset);
 
+/* ---- run-time switches and debug taps (no reference counterpart; used by the parity tests and A/B measurements) ----
+ * Options are per handle; changing one drops the cached launch plans.  Defaults come from the environment variables of
+ * the same meaning (VITDET_FUSE_LN, VITDET_FUSE_TAIL, VITDET_GEMM_PAIR, VITDET_ATTN) and otherwise are the product path.
+ *   "fuse_ln"    1 (default): LayerNorm runs in the epilogue of the GEMM that produces the residual-stream row; 0: stand-alone kernel
+ *   "fuse_tail"  1 (default): the last three MLP layers of a block run as one kernel; 0: three GEMM launches
+ *   "gemm_pair"  1 (default): CTA-pair GEMM for K >= 512 layers; 0: never; 2: wherever it is legal
+ *   "attention"  40 (default): persistent kernel (attention_tcp.cu); 4: one CTA per 128-query work item (attention_tc.cu);
+ *                8: score rows split over warp pairs (attention_tc8.cu) */
+int vitdet_set_option(vitdet_handle* h, const char* key, int value);
+int vitdet_get_option(const vitdet_handle* h, const char* key, int* value);
+
+/* Debug taps: while enabled, every forward also keeps a copy of the float32 residual stream after the patch embedding
+ * ("embedded_patches", det.py:305-307) and after every encoder block ("block_1" ... "block_L", det.py:408-412), plus
+ * "head_last" = the input of MLP_Head_no_Sigmoid (det.py:489).  vitdet_debug_read copies one tap of the LAST forward to
+ * a HOST float32 array: [B*tokens, embedding_dim] (or [B*num_slots, head_last_units] for "head_last"); synchronises. */
+int vitdet_debug_taps(vitdet_handle* h, int enable);
+int vitdet_debug_read(vitdet_handle* h, const char* name, float* out_host, int64_t capacity);
+
 /* Replaces model.predict(x) / model(x, training=False):
  * images_dev: DEVICE float32 NHWC [B, image_h, image_w, 3]; logits_dev: DEVICE float32 [B, num_slots, 6]
  * raw logits (the output of 'MLP_Head_no_Sigmoid', det.py:489-493). */
@@ -268,6 +286,35 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
                         int d, int mode, void* stream);
 /* tf.image.extract_patches(SAME) + Reshape: images [B,H,W,3] f32 -> patches [B*T, 3*p*p] f32. */
 int vitdet_op_patchify(const float* images, int B, int H, int W, int p, float* patches, void* stream);
+
+/* Extras of the tensor-core Dense epilogue that the plain call above does not reach (bf16 mode only):
+ *   pos / pos_period     per-row scalar pos[m % pos_period] added before the activation (the position embedding fused
+ *                        into the linear_projection GEMM, det.py:291-307); NULL = none
+ *   ln_gamma, ln_beta, ln_eps, ln_out
+ *                        fused LayerNormalization of the finished output row (N <= 32 only): ln_out [M,N] receives, as
+ *                        float32, the bf16 values the kernel hands to the next GEMM; NULL = none
+ *   store_bf16           1: run the bf16-output epilogue (bias + activation on packed pairs, TMA store) and widen the stored
+ *                        bf16 result to float32 in `out`; resid must be NULL.  0: the float32-output epilogue
+ *   pair                 -1: choose as the forward pass does; 0: single-CTA kernel; 1: CTA-pair kernel */
+typedef struct vitdet_dense_ex {
+    const float* pos; int32_t pos_period;
+    const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_out;
+    int32_t store_bf16;
+    int32_t pair;
+} vitdet_dense_ex;
+int vitdet_op_dense_ex(const float* A, const float* kernel, const float* bias, const float* resid, float* out,
+                       int M, int K, int N, int act, const vitdet_dense_ex* ex, void* stream);
+/* The fused tail of the encoder MLP pyramid (csrc/mlp_tail.cu; det.py:388-412 for the last three layers + the next
+ * block's LayerNormalization det.py:353): x += act(act(act(A W0 + b0) W1 + b1) W2 + b2), ln_out = LN(x).
+ * A [M,K0], kernels in Keras layout W0 [K0,N0], W1 [N0,N1], W2 [N1,N2], x [M,N2] float32 in/out, ln_out [M,N2] float32
+ * (widened bf16) or NULL with ln_gamma/ln_beta.  Fails with VITDET_E_INVALID for widths the kernel does not take. */
+int vitdet_op_mlp_tail(const float* A, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                       const float* b2, float* x, const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
+                       int M, int K0, int N0, int N1, int N2, int act, void* stream);
+/* mlp_head first stage (det.py:454-463): Dense(D -> S) on every token of `images` images of `tokens` tokens, stored as the
+ * reference's Reshape((S, -1)) lays it out: out [images*S, tokens] float32 (mode bf16: widened from the stored bf16). */
+int vitdet_op_head_slots(const float* x, const float* kernel, const float* bias, float* out, int images, int tokens, int D,
+                         int S, int mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -379,3 +379,77 @@ def weights_to_torch(weights: dict) -> dict:
     """Pre-converts a weight dict once so that repeated timed forward_torch_f32 calls do not pay for it."""
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in weights.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16-faithful mode: the product's bf16 data path restated with float64 accumulation
+# ------------------------------------------------------------------------------------------------
+def bf16_round(x) -> np.ndarray:
+    """Round to the nearest bfloat16 (ties to even), returned as float64.  Matches cvt.rn.bf16.f32 /
+    __float2bfloat16_rn on the float32 value of x (NaN/Inf pass through)."""
+    f = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    u = f.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    out = (r & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+    out = np.where(np.isfinite(f), out, f)
+    return out.astype(np.float64).reshape(np.shape(x))
+
+
+def attention_core_bf16(q: np.ndarray, k: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """attention_core with the operand roundings of the tensor-core kernel: q, k, v are bf16 values; the scores and the
+    softmax statistics are float (float64 here); the probabilities fed to the P.V product are rounded to bf16 while the
+    row sum uses the unrounded ones; the result is divided by that sum (csrc/attention_tc8.cu)."""
+    d = q.shape[-1]
+    s = np.einsum("aecd,abcd->acbe", k, q) * (1.0 / math.sqrt(d))
+    s = s - s.max(axis=-1, keepdims=True)
+    e = np.exp(s)
+    o = np.einsum("acbe,aecd->abcd", bf16_round(e), v)
+    return o / np.moveaxis(e.sum(axis=-1), 1, 2)[..., None]
+
+
+def forward_bf16(weights: dict, cfg, images: np.ndarray, return_intermediates: bool = False):
+    """The forward pass with every operand rounding of the product's bf16 mode and float64 accumulation:
+    bf16 patches and Dense weights, float32-like (here float64) residual stream, bf16 LayerNorm outputs, bf16 q/k/v and
+    attention context, bf16 activations between the MLP / head layers, float weights for the slot projection and the
+    final Dense(6).  A tensor-core kernel with a dropped k-tail, a wrong swizzle column or a mis-fused LayerNorm differs
+    from this by far more than the accumulation-order noise (~1e-3) that separates a correct one from it."""
+    w64 = {k: np.asarray(v, dtype=np.float64) for k, v in weights.items()}
+    wb = {k: bf16_round(v) for k, v in weights.items()}
+    act = mish if _cfg(cfg, "use_mish", True) else gelu_tanh
+    p = _cfg(cfg, "patch_size")
+    L, qn = _cfg(cfg, "encoder_repeat_times"), _cfg(cfg, "encoder_mlp_quantities")
+    inter = {}
+    x = bf16_round(extract_patches(np.asarray(images, dtype=np.float32), p))
+    x = x @ wb["linear_projection/kernel"] + w64["linear_projection/bias"]
+    x = x + w64["position_encoding/position_embedding/embeddings"][None, :, :]
+    inter["embedded_patches"] = x
+    for i in range(L):
+        ln1, ln2, mha = _kname("layer_normalization", 2 * i), _kname("layer_normalization", 2 * i + 1), _kname("multi_head_attention", i)
+        y = bf16_round(layer_norm(x, w64[ln1 + "/gamma"], w64[ln1 + "/beta"]))
+        q = bf16_round(np.einsum("abc,cde->abde", y, wb[mha + "/query/kernel"]) + w64[mha + "/query/bias"])
+        k = bf16_round(np.einsum("abc,cde->abde", y, wb[mha + "/key/kernel"]) + w64[mha + "/key/bias"])
+        v = bf16_round(np.einsum("abc,cde->abde", y, wb[mha + "/value/kernel"]) + w64[mha + "/value/bias"])
+        o = bf16_round(attention_core_bf16(q, k, v))
+        x = np.einsum("abcd,cde->abe", o, wb[mha + "/attention_output/kernel"]) + w64[mha + "/attention_output/bias"] + x
+        y = bf16_round(layer_norm(x, w64[ln2 + "/gamma"], w64[ln2 + "/beta"]))
+        for j in range(qn):
+            y = act(y @ wb[f"MLP_{i + 1}_{j + 1}/kernel"] + w64[f"MLP_{i + 1}_{j + 1}/bias"])
+            if j + 1 < qn:
+                y = bf16_round(y)
+        x = y + x
+        inter[f"block_{i + 1}"] = x
+    inter["encoded_images"] = x
+    B = x.shape[0]
+    kk = 0
+    y = bf16_round(x @ w64[_kname("dense", kk) + "/kernel"] + w64[_kname("dense", kk) + "/bias"])      # float weights, bf16 store
+    kk += 1
+    y = y.reshape(B, SLOTS, -1)
+    n, rep = _cfg(cfg, "mlp_head_dense_layers_quantity"), _cfg(cfg, "mlp_head_dense_mish_block_repeats")
+    for _ in range(n * rep):
+        y = bf16_round(act(y @ wb[_kname("dense", kk) + "/kernel"] + w64[_kname("dense", kk) + "/bias"]))
+        kk += 1
+    inter["head_last"] = y
+    logits = y @ w64["MLP_Head_no_Sigmoid/kernel"] + w64["MLP_Head_no_Sigmoid/bias"]
+    if return_intermediates:
+        return logits, inter
+    return logits

@@ -80,3 +80,22 @@ def map_case(seed, batch, slots, classes_used=(3, 17, 79), exact_class=0.5, max_
             y_pred[b, ps] = [rng.uniform(0.4, 1.0), np.clip(cls, 0, 79), rng.uniform(0, image), rng.uniform(0, image),
                              rng.uniform(10, 200), rng.uniform(10, 200)]
     return y_true, y_pred
+
+
+TF_GOLDEN = os.path.join(ROOT, "tests", "golden", "tf_forward.npz")
+
+
+def load_tf_golden(path=TF_GOLDEN) -> dict:
+    """Reads a file written by tools/make_tf_golden.py (outputs of the unmodified reference under TensorFlow 2.9)."""
+    import json
+    out = {}
+    with np.load(path, allow_pickle=False) as z:
+        for name in json.loads(str(z["cases"])):
+            names = json.loads(str(z[f"{name}/weight_names"]))
+            kwargs = json.loads(str(z[f"{name}/kwargs"]))
+            if "input_shape" in kwargs:
+                kwargs["input_shape"] = tuple(kwargs["input_shape"])
+            taps = {k.split("/tap/")[1]: z[k] for k in z.files if k.startswith(f"{name}/tap/")}
+            out[name] = dict(kwargs=kwargs, weight_names=names, weights=[z[f"{name}/w/{i}"] for i in range(len(names))],
+                             images=z[f"{name}/images"], logits=z[f"{name}/logits"], decoded=z[f"{name}/decoded"], taps=taps)
+    return out

@@ -50,6 +50,15 @@ class DecodeParams(C.Structure):
     ]
 
 
+class DenseEx(C.Structure):
+    """struct vitdet_dense_ex — extras of the tensor-core Dense epilogue (operator-level tests)."""
+    _fields_ = [
+        ("pos", C.c_void_p), ("pos_period", C.c_int32),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_out", C.c_void_p),
+        ("store_bf16", C.c_int32), ("pair", C.c_int32),
+    ]
+
+
 class Detections(C.Structure):
     """struct vitdet_detections (device or host pointers depending on the call)."""
     _fields_ = [
@@ -105,6 +114,13 @@ SYMBOLS = {
     "vitdet_op_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "vitdet_op_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vitdet_op_patchify": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vitdet_op_dense_ex": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DenseEx), _P]),
+    "vitdet_op_mlp_tail": (C.c_int, [_P] * 8 + [_P, _P, C.c_float, _P] + [C.c_int] * 6 + [_P]),
+    "vitdet_op_head_slots": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitdet_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "vitdet_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int)]),
+    "vitdet_debug_taps": (C.c_int, [_P, C.c_int]),
+    "vitdet_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
 }
 
 _lib = None

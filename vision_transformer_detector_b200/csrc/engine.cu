@@ -55,7 +55,29 @@ constexpr int kMaxKeyDim = 64;    // one 128-byte swizzle row of bf16 per head i
 // attention kernel's tensor map zero-fills columns hp..63 of every head tile, so HBM carries no 64-wide pad.
 static inline int head_pitch(int key_dim) { return (key_dim + 7) / 8 * 8; }
 
-static cudaError_t attn_launch(const AttnPlan& plan, cudaStream_t st) { return attn_tc_launch(plan, st); }
+// Run-time switches of one handle (vitdet_set_option); the defaults are the product path unless the environment
+// variable of the same meaning says otherwise (A/B scripts).
+struct Options {
+    int fuse_ln = 1;       // VITDET_FUSE_LN=0: stand-alone LayerNorm kernel
+    int fuse_tail = 1;     // VITDET_FUSE_TAIL=0: the last three MLP layers as separate GEMM launches
+    int gemm_pair = 1;     // VITDET_GEMM_PAIR=0 never / all (2) wherever legal / default: K >= 512 layers
+    int attention = 40;    // VITDET_ATTN: 40 persistent kernel (attention_tcp.cu), 4 one CTA per work item (attention_tc.cu), 8 split score rows (attention_tc8.cu)
+};
+
+static Options env_options() {
+    Options o;
+    if (const char* e = getenv("VITDET_FUSE_LN")) o.fuse_ln = strcmp(e, "0") != 0;
+    if (const char* e = getenv("VITDET_FUSE_TAIL")) o.fuse_tail = strcmp(e, "0") != 0;
+    if (const char* e = getenv("VITDET_GEMM_PAIR")) o.gemm_pair = strcmp(e, "0") == 0 ? 0 : (strcmp(e, "all") == 0 ? 2 : 1);
+    if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 40) o.attention = v; }
+    return o;
+}
+
+static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, cudaStream_t st) {
+    if (version == 4) return attn_tc_launch(plan, st);
+    if (version == 8) return attn_tc8_launch(plan, st);
+    return attn_tcp_launch(plan, num_sms, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // weight packing kernels (run once per set_weight)
@@ -199,6 +221,7 @@ struct vitdet_handle {
     int RP = 0, PK = 0;                 // run pitch of one patch row (round_up(3p, 4)) and padded patch vector p * RP
     int act = ACT_MISH;
     int chunk = 64;
+    Options opt;
 
     // weights
     DenseW proj;
@@ -230,6 +253,14 @@ struct vitdet_handle {
         std::vector<TcGemmPlan> dense;
     };
     std::map<int, HeadPlans> head_plans;    // key: batch
+
+    // debug taps (vitdet_debug_taps): residual stream after the patch embedding and after every block, of the last forward
+    int s_layout_mode = -1;             // arithmetic mode the slot matrix `s` was last laid out for (its pad columns are zeroed per layout)
+    bool taps_on = false;
+    DevBuf taps;                        // f32 [(L + 1)][B*T, D4]
+    int taps_B = 0;
+    const void* head_last = nullptr;    // input of the final Dense(6) in the last forward: [taps_B*S, head_last_ld]
+    int head_last_ld = 0, head_last_f32 = 0;
 
     // profiling (off by default): CUDA events around the launches of the categories in prof_mask
     uint32_t prof_mask = 0;
@@ -428,35 +459,25 @@ static GemmDesc make_desc(const DenseCall& c, int mode) {
 // is legal (A/B measurements and tests).
 // Measured (B = 64): 3 % faster on the MMA-bound layers (3584 -> 1792 -> 896 -> 448), slower on the K = 28
 // layers whose time is the epilogue (the pair couples both CTAs' epilogues), hence the K threshold.
-static bool use_pair_kernel(int M, int N, int K) {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VITDET_GEMM_PAIR"); v = (e && strcmp(e, "0") == 0) ? 0 : (e && strcmp(e, "all") == 0) ? 2 : 1; }
-    if (v == 0 || M < 1024 || N < 128) return false;
-    return v == 2 || K >= 512;
+static bool pair_kernel_legal(const GemmDesc& g) { return g.M >= 1024 && g.N >= 128 && !g.ln_out; }
+
+static bool use_pair_kernel(int pair_mode, const GemmDesc& g) {
+    if (pair_mode == 0 || !pair_kernel_legal(g)) return false;
+    return pair_mode == 2 || g.K >= 512;
 }
 
-static int make_tc_plan(TcGemmPlan* plan, const GemmDesc& g, int num_sms) {
-    plan->pair = use_pair_kernel(g.M, g.N, g.K) ? 1 : 0;
+static int make_tc_plan(TcGemmPlan* plan, const GemmDesc& g, int num_sms, int pair_mode) {
+    plan->pair = use_pair_kernel(pair_mode, g) ? 1 : 0;
     return plan->pair ? tc2_gemm_make_plan(plan, g, num_sms) : tc_gemm_make_plan(plan, g, num_sms);
 }
 
-// VITDET_FUSE_LN=0 keeps the stand-alone LayerNorm kernel (A/B measurements).
-static bool ln_is_fused(const vitdet_handle* h) {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VITDET_FUSE_LN"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
-    return v == 1 && h->D <= 32;
-}
-
-// VITDET_FUSE_TAIL=0 keeps the last three MLP layers as separate GEMM launches (A/B measurements).
-static bool tail_fusion_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("VITDET_FUSE_TAIL"); v = (e && strcmp(e, "0") == 0) ? 0 : 1; }
-    return v == 1;
-}
+// The fused LayerNorm needs the whole residual-stream row in one epilogue thread (D <= 32).
+static bool ln_is_fused(const vitdet_handle* h) { return h->opt.fuse_ln && h->D <= 32; }
+static bool tail_fusion_enabled(const vitdet_handle* h) { return h->opt.fuse_tail != 0; }
 
 static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
     GemmDesc g = make_desc(c, VITDET_MODE_BF16);
-    int rc = make_tc_plan(plan, g, h->num_sms);
+    int rc = make_tc_plan(plan, g, h->num_sms, h->opt.gemm_pair);
     if (rc) return fail(VITDET_E_INVALID, "tc_gemm_make_plan(M=%d N=%d K=%d lda=%d ldc=%d) failed: %d", g.M, g.N, g.K, g.lda, g.ldc, rc);
     return 0;
 }
@@ -467,6 +488,7 @@ static int plan_dense(vitdet_handle* h, const DenseCall& c, TcGemmPlan* plan) {
 struct Dims {
     int es;          // activation element size
     int D4, D8, Pld, w_qkv, w_ctx, w_u0, w_u1, w_h0, w_h1;
+    int Tp;          // row pitch of the slot matrix s [B*S, T]: T rounded up to a 16-byte multiple (pads stay zero)
 };
 
 static Dims dims_for(const vitdet_handle* h, int mode) {
@@ -476,6 +498,7 @@ static Dims dims_for(const vitdet_handle* h, int mode) {
     m.D4 = round_up(h->D, 4);
     m.D8 = round_up(h->D, 8);
     m.Pld = round_up(h->PK, 8);
+    m.Tp = round_up(h->T, mode == VITDET_MODE_BF16 ? 8 : 4);
     m.w_qkv = 3 * h->H * h->hp;
     m.w_ctx = h->H * h->hp;
     // MLP ping-pong: layer j writes buffer j & 1; widest even / odd layer outputs.
@@ -502,7 +525,7 @@ static size_t workspace_bytes(const vitdet_handle* h, int B, int mode) {
     tot += a256(static_cast<size_t>(B) * h->T * m.D4 * 4);
     tot += a256(Mc * m.Pld * m.es) + a256(Mc * m.D8 * m.es) + a256(Mc * m.w_qkv * m.es) + a256(Mc * m.w_ctx * m.es);
     tot += a256(Mc * m.w_u0 * m.es) + a256(Mc * m.w_u1 * m.es);
-    tot += a256(R * h->T * m.es) + a256(R * m.w_h0 * m.es) + a256(R * m.w_h1 * m.es);
+    tot += a256(R * m.Tp * m.es) + a256(R * m.w_h0 * m.es) + a256(R * m.w_h1 * m.es);
     return tot;
 }
 
@@ -518,7 +541,13 @@ static int ensure_workspace(vitdet_handle* h, int B, int mode) {
     RC_TRY(h->ctx.ensure(Mc * m.w_ctx * m.es));
     RC_TRY(h->u0.ensure(Mc * m.w_u0 * m.es));
     RC_TRY(h->u1.ensure(Mc * m.w_u1 * m.es));
-    RC_TRY(h->s.ensure(R * h->T * m.es));
+    {
+        const void* s_before = h->s.p; const size_t s_bytes = h->s.bytes;
+        RC_TRY(h->s.ensure(R * m.Tp * m.es));
+        // the pad columns [T, Tp) of every row are read by the first head GEMM's last k-step and never written
+        if (m.Tp != h->T && (h->s.p != s_before || h->s.bytes != s_bytes || h->s_layout_mode != mode)) { CU_TRY(cudaMemset(h->s.p, 0, h->s.bytes)); CU_TRY(cudaDeviceSynchronize()); }
+        h->s_layout_mode = mode;
+    }
     RC_TRY(h->h0.ensure(R * m.w_h0 * m.es));
     RC_TRY(h->h1.ensure(R * m.w_h1 * m.es));
     const void* after[10] = {h->x.p, h->patch.p, h->y.p, h->qkv.p, h->ctx.p, h->u0.p, h->u1.p, h->s.p, h->h0.p, h->h1.p};
@@ -567,7 +596,7 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
         RC_TRY(plan_dense(h, with_ln(oc, b.ln2_g, b.ln2_b), &ep->out[i]));
         // The last three layers fuse into one kernel when their widths fit it (default model: 224 -> 112 -> 56 -> 28).
         bool tail = false;
-        if (fuse_ln && tail_fusion_enabled() && q >= 4) {
+        if (fuse_ln && tail_fusion_enabled(h) && q >= 4) {
             const int N3[3] = {b.mlp[q - 3].N, b.mlp[q - 2].N, b.mlp[q - 1].N};
             const int K3[3] = {b.mlp[q - 3].K, b.mlp[q - 2].K, b.mlp[q - 1].K};
             tail = mlp_tail_supported(N3, K3);
@@ -608,7 +637,7 @@ static int build_enc_plans(vitdet_handle* h, int bc, vitdet_handle::EncPlans* ep
 static int build_head_plans(vitdet_handle* h, int B, vitdet_handle::HeadPlans* hp) {
     const int R = B * h->S;
     hp->dense.resize(h->head.size());
-    const void* a = h->s.p; int lda = h->T;
+    const void* a = h->s.p; int lda = dims_for(h, VITDET_MODE_BF16).Tp;
     for (size_t i = 0; i < h->head.size(); ++i) {
         void* o = (i & 1) ? h->h1.p : h->h0.p;
         const int ldo = round_up(h->head[i].N, 8);
@@ -710,12 +739,18 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
         if (!s.set) return fail(VITDET_E_UNSET, "forward: weight '%s' has not been set", s.name.c_str());
     const vitdet_config& c = h->cfg;
     const bool bf = mode == VITDET_MODE_BF16;
-    if (bf && (h->T % 8)) return fail(VITDET_E_INVALID, "bf16 mode needs tokens %% 8 == 0 (tokens = %d)", h->T);
-    if (!bf && (h->T % 4)) return fail(VITDET_E_INVALID, "fp32 mode needs tokens %% 4 == 0 (tokens = %d)", h->T);
     RC_TRY(ensure_workspace(h, B, mode));
     const Dims m = dims_for(h, mode);
     const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
     const int out_f32_act = bf ? 0 : 1;
+    const size_t tap_stride = static_cast<size_t>(B) * T * m.D4;      // floats per tap
+    if (h->taps_on) { RC_TRY(h->taps.ensure(static_cast<size_t>(L + 1) * tap_stride * 4)); h->taps_B = B; }
+    auto tap = [&](int index, const float* xc, int c0, int bc) -> int {
+        if (!h->taps_on) return 0;
+        CU_TRY(cudaMemcpyAsync(h->taps.as<float>() + index * tap_stride + static_cast<size_t>(c0) * T * m.D4, xc,
+                               static_cast<size_t>(bc) * T * m.D4 * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    };
 
     for (int c0 = 0, bc = 0, ci = 0; c0 < B; c0 += bc, ++ci) {
         bc = (B - c0) < h->chunk ? (B - c0) : h->chunk;
@@ -739,6 +774,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
             DenseCall pc{h->patch.p, round_up(h->PK, 4), &h->proj, h->pos.as<float>(), T, nullptr, 0, x, m.D4, 1, ACT_NONE, Mc};
             RC_TRY(launch_simt(pc, st));
         }
+        RC_TRY(tap(0, x, c0, bc));
         for (int i = 0; i < L; ++i) {
             BlockW& b = h->blocks[i];
             const int ldy = bf ? m.D8 : m.D4;
@@ -746,7 +782,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
             CU_TRY(layernorm_launch(x, m.D4, b.ln1_g.as<float>(), b.ln1_b.as<float>(), Mc, h->D, c.ln_epsilon, h->y.p, ldy, out_f32_act, st)); }
             if (bf) {
                 { ProfScope ps(h, PC_QKV, st); RC_TRY(launch_tc(ep->qkv[i], h->qkv.p, nullptr, st)); }
-                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_launch(ep->attn[i], st)); }
+                { ProfScope ps(h, PC_ATTN, st); CU_TRY(attn_launch(h->opt.attention, ep->attn[i], h->num_sms, st)); }
                 { ProfScope ps(h, PC_OUT, st); RC_TRY(launch_tc(ep->out[i], x, x, st)); }
             } else {
                 DenseCall qc{h->y.p, ldy, &b.qkv, nullptr, 1, nullptr, 0, h->qkv.p, m.w_qkv, 1, ACT_NONE, Mc};
@@ -782,6 +818,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
                     a = o; lda = ldo;
                 }
             }
+            RC_TRY(tap(i + 1, x, c0, bc));
         }
     }
 
@@ -789,8 +826,8 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
     const int R = B * h->S;
     { ProfScope ps(h, PC_HEAD_SLOTS, st);
     CU_TRY(head_slots_launch(h->x.as<float>(), m.D4, h->head_slot_w.as<float>(), h->head_slot_b.as<float>(), B * T, h->D, h->S,
-                             h->s.p, out_f32_act, st)); }
-    const void* a = h->s.p; int lda = T;
+                             T, m.Tp, h->s.p, out_f32_act, st)); }
+    const void* a = h->s.p; int lda = m.Tp;
     if (bf) {
         vitdet_handle::HeadPlans* hp = &h->head_plans[B];
         if (!hp->valid) RC_TRY(build_head_plans(h, B, hp));
@@ -823,6 +860,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
         dout.decoded = det->decoded; dout.class_id = det->class_id; dout.class_conf = det->class_conf;
         dout.keep = det->keep; dout.corners = det->corners;
     }
+    h->head_last = a; h->head_last_ld = lda; h->head_last_f32 = out_f32_act;
     ProfScope ps(h, PC_HEAD_TAIL, st);
     CU_TRY(head_tail_launch(a, lda, out_f32_act, h->tail_w.as<float>(), h->tail_b.as<float>(), R, h->tail_U, dp, dout, st));
     return 0;
@@ -885,6 +923,7 @@ int vitdet_create(const vitdet_config* cfg, vitdet_handle** out) {
     h->D = c.embedding_dim; h->H = c.num_heads; h->d = c.key_dim; h->S = c.num_slots;
     h->hp = head_pitch(c.key_dim);
     h->act = c.use_mish ? ACT_MISH : ACT_GELU;
+    h->opt = env_options();
     int rc = build_weight_table(h);
     if (rc) { delete h; return rc; }
     *out = h;
@@ -915,6 +954,12 @@ int vitdet_weight_info(const vitdet_handle* h, int index, char* name, int cap, i
 
 int vitdet_set_weight(vitdet_handle* h, const char* name_in, const float* data, int ndim, const int64_t* shape) {
     if (!h || !name_in || !data) return fail(VITDET_E_INVALID, "set_weight: null argument");
+    {
+        int cur = -1;
+        CU_TRY(cudaGetDevice(&cur));
+        if (cur != h->device)
+            return fail(VITDET_E_INVALID, "set_weight: the handle lives on device %d but the current CUDA device is %d", h->device, cur);
+    }
     std::string name(name_in);
     if (name.size() > 2 && name.compare(name.size() - 2, 2, ":0") == 0) name.resize(name.size() - 2);
     auto it = h->slot_index.find(name);
@@ -988,6 +1033,70 @@ int64_t vitdet_launch_count(vitdet_handle* h, int reset) {
     const long long n = h->launches;
     if (reset) h->launches = 0;
     return n;
+}
+
+int vitdet_set_option(vitdet_handle* h, const char* key, int value) {
+    if (!h || !key) return fail(VITDET_E_INVALID, "set_option: null argument");
+    const std::string k(key);
+    if (k == "fuse_ln") h->opt.fuse_ln = value != 0;
+    else if (k == "fuse_tail") h->opt.fuse_tail = value != 0;
+    else if (k == "gemm_pair") { if (value < 0 || value > 2) return fail(VITDET_E_INVALID, "set_option(gemm_pair): 0, 1 or 2"); h->opt.gemm_pair = value; }
+    else if (k == "attention") { if (value != 4 && value != 8 && value != 40) return fail(VITDET_E_INVALID, "set_option(attention): 4, 8 or 40"); h->opt.attention = value; }
+    else return fail(VITDET_E_NOT_FOUND, "set_option: unknown option '%s'", key);
+    h->enc_plans.clear();
+    h->head_plans.clear();
+    return 0;
+}
+
+int vitdet_get_option(const vitdet_handle* h, const char* key, int* value) {
+    if (!h || !key || !value) return fail(VITDET_E_INVALID, "get_option: null argument");
+    const std::string k(key);
+    if (k == "fuse_ln") *value = h->opt.fuse_ln;
+    else if (k == "fuse_tail") *value = h->opt.fuse_tail;
+    else if (k == "gemm_pair") *value = h->opt.gemm_pair;
+    else if (k == "attention") *value = h->opt.attention;
+    else return fail(VITDET_E_NOT_FOUND, "get_option: unknown option '%s'", key);
+    return 0;
+}
+
+int vitdet_debug_taps(vitdet_handle* h, int enable) {
+    if (!h) return fail(VITDET_E_INVALID, "debug_taps: null handle");
+    h->taps_on = enable != 0;
+    if (!h->taps_on) h->taps_B = 0;
+    return 0;
+}
+
+int vitdet_debug_read(vitdet_handle* h, const char* name, float* out_host, int64_t capacity) {
+    if (!h || !name || !out_host) return fail(VITDET_E_INVALID, "debug_read: null argument");
+    if (!h->taps_on || h->taps_B <= 0) return fail(VITDET_E_UNSET, "debug_read: no forward has run with the taps enabled");
+    const std::string k(name);
+    CU_TRY(cudaDeviceSynchronize());
+    const int B = h->taps_B;
+    if (k == "head_last") {
+        const int64_t R = static_cast<int64_t>(B) * h->S, U = h->tail_U;
+        if (capacity < R * U) return fail(VITDET_E_SHAPE, "debug_read(head_last): capacity %lld < %lld", (long long)capacity, (long long)(R * U));
+        const size_t es = h->head_last_f32 ? 4 : 2;
+        std::vector<char> raw(static_cast<size_t>(R) * h->head_last_ld * es);
+        CU_TRY(cudaMemcpy(raw.data(), h->head_last, raw.size(), cudaMemcpyDeviceToHost));
+        for (int64_t r = 0; r < R; ++r)
+            for (int64_t u = 0; u < U; ++u) {
+                const size_t i = static_cast<size_t>(r) * h->head_last_ld + u;
+                out_host[r * U + u] = h->head_last_f32 ? reinterpret_cast<const float*>(raw.data())[i]
+                                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(raw.data())[i]);
+            }
+        return 0;
+    }
+    int index = -1;
+    if (k == "embedded_patches") index = 0;
+    else if (k.compare(0, 6, "block_") == 0) index = atoi(k.c_str() + 6);
+    if (index < 0 || index > h->cfg.repeat_times || (index == 0 && k != "embedded_patches"))
+        return fail(VITDET_E_NOT_FOUND, "debug_read: unknown tap '%s'", name);
+    const int D4 = round_up(h->D, 4);
+    const int64_t rows = static_cast<int64_t>(B) * h->T;
+    if (capacity < rows * h->D) return fail(VITDET_E_SHAPE, "debug_read('%s'): capacity %lld < %lld", name, (long long)capacity, (long long)(rows * h->D));
+    CU_TRY(cudaMemcpy2D(out_host, static_cast<size_t>(h->D) * 4, h->taps.as<float>() + static_cast<size_t>(index) * rows * D4,
+                        static_cast<size_t>(D4) * 4, static_cast<size_t>(h->D) * 4, static_cast<size_t>(rows), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int vitdet_set_chunk(vitdet_handle* h, int n) {
@@ -1240,7 +1349,7 @@ int vitdet_op_dense(const float* A, const float* kernel, const float* bias, cons
         DenseCall c{a_buf.p, K8, &w, nullptr, 1, rp, N4, o_buf.p, N4, 1, act, M};
         TcGemmPlan plan;
         GemmDesc g = make_desc(c, VITDET_MODE_BF16);
-        rc = make_tc_plan(&plan, g, sms);
+        rc = make_tc_plan(&plan, g, sms, env_options().gemm_pair);
         if (rc) return fail(VITDET_E_INVALID, "op_dense: tc_gemm_make_plan failed: %d", rc);
         RC_TRY(launch_tc(plan, o_buf.p, rp, st));
     } else {
@@ -1294,13 +1403,134 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
         AttnPlan plan;
         int rc = attn_bf16_make_plan(&plan, ad);
         if (rc) return fail(VITDET_E_INVALID, "op_attention: attn_bf16_make_plan failed: %d", rc);
-        CU_TRY(attn_launch(plan, st));
+        { int dev2 = 0, sms2 = 148; CU_TRY(cudaGetDevice(&dev2)); CU_TRY(cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2));
+          CU_TRY(attn_launch(env_options().attention, plan, sms2, st)); }
         unpack_ctx_kernel<__nv_bfloat16><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<__nv_bfloat16>(), rows, H, d, hp, out);
     } else {
         pack_qkv_kernel<float><<<blocks_for(rows * 3 * H * hp), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<float>());
         CU_TRY(attn_f32_launch(ad, st));
         unpack_ctx_kernel<float><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<float>(), rows, H, d, hp, out);
     }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+__global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int lds, float* __restrict__ dst) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(rows) * cols) return;
+    const int r = static_cast<int>(idx / cols), c = static_cast<int>(idx - static_cast<long long>(r) * cols);
+    dst[idx] = __bfloat162float(src[static_cast<size_t>(r) * lds + c]);
+}
+
+int vitdet_op_dense_ex(const float* A, const float* kernel, const float* bias, const float* resid, float* out, int M, int K,
+                       int N, int act, const vitdet_dense_ex* ex, void* stream) {
+    if (!A || !kernel || !out || !ex || M <= 0 || K <= 0 || N <= 0) return fail(VITDET_E_INVALID, "op_dense_ex: bad arguments");
+    if (ex->store_bf16 && (resid || ex->pos || ex->ln_out)) return fail(VITDET_E_INVALID, "op_dense_ex: store_bf16 excludes resid / pos / ln_out");
+    if (ex->ln_out && (N > 32 || !ex->ln_gamma || !ex->ln_beta)) return fail(VITDET_E_INVALID, "op_dense_ex: the fused LayerNorm needs N <= 32, gamma and beta");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DenseW w;
+    RC_TRY(w.alloc(N, K));
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16,
+                                                                               w.w32.as<float>(), w.ld32);
+    if (bias) CU_TRY(cudaMemcpyAsync(w.bias.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, st));
+    const int N4 = round_up(N, 4), N8 = round_up(N, 8), K8 = round_up(K, 8);
+    DevBuf a_buf, o_buf, r_buf, ln_buf;
+    RC_TRY(a_buf.ensure(static_cast<size_t>(M) * K8 * 2));
+    f32_to_bf16_kernel<<<blocks_for(static_cast<long long>(M) * K8), 256, 0, st>>>(A, M, K, K, a_buf.as<__nv_bfloat16>(), K8);
+    const float* rp = nullptr;
+    if (resid) {
+        RC_TRY(r_buf.ensure(static_cast<size_t>(M) * N4 * 4));
+        pad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * N4), 256, 0, st>>>(resid, M, N, N, r_buf.as<float>(), N4);
+        rp = r_buf.as<float>();
+    }
+    const int ldc = ex->store_bf16 ? N8 : N4;
+    RC_TRY(o_buf.ensure(static_cast<size_t>(M) * ldc * (ex->store_bf16 ? 2 : 4)));
+    DenseCall c{a_buf.p, K8, &w, ex->pos, ex->pos_period > 0 ? ex->pos_period : 1, rp, N4, o_buf.p, ldc, ex->store_bf16 ? 0 : 1, act, M};
+    if (ex->ln_out) {
+        RC_TRY(ln_buf.ensure(static_cast<size_t>(M) * N8 * 2));
+        c.ln_gamma = ex->ln_gamma; c.ln_beta = ex->ln_beta; c.ln_eps = ex->ln_eps; c.ln_out = ln_buf.p; c.ln_ld = N8;
+    }
+    TcGemmPlan plan;
+    GemmDesc g = make_desc(c, VITDET_MODE_BF16);
+    if (ex->pair > 0 && !pair_kernel_legal(g)) return fail(VITDET_E_INVALID, "op_dense_ex: the CTA-pair kernel needs M >= 1024, N >= 128 and no fused LayerNorm");
+    int rc = make_tc_plan(&plan, g, sms, ex->pair < 0 ? env_options().gemm_pair : (ex->pair ? 2 : 0));
+    if (rc) return fail(VITDET_E_INVALID, "op_dense_ex: tc_gemm_make_plan failed: %d", rc);
+    RC_TRY(launch_tc(plan, o_buf.p, rp, st));
+    if (ex->store_bf16) bf16_rows_to_f32_kernel<<<blocks_for(static_cast<long long>(M) * N), 256, 0, st>>>(o_buf.as<__nv_bfloat16>(), M, N, N8, out);
+    else unpad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * N), 256, 0, st>>>(o_buf.as<float>(), M, N, N4, out);
+    if (ex->ln_out) bf16_rows_to_f32_kernel<<<blocks_for(static_cast<long long>(M) * N), 256, 0, st>>>(ln_buf.as<__nv_bfloat16>(), M, N, N8, ex->ln_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vitdet_op_mlp_tail(const float* A, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                       const float* b2, float* x, const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
+                       int M, int K0, int N0, int N1, int N2, int act, void* stream) {
+    if (!A || !W0 || !W1 || !W2 || !b0 || !b1 || !b2 || !x || M <= 0) return fail(VITDET_E_INVALID, "op_mlp_tail: bad arguments");
+    if (ln_out && (!ln_gamma || !ln_beta)) return fail(VITDET_E_INVALID, "op_mlp_tail: ln_out needs gamma and beta");
+    const int N[3] = {N0, N1, N2}, K[3] = {K0, N0, N1};
+    if (!mlp_tail_supported(N, K)) return fail(VITDET_E_INVALID, "op_mlp_tail: widths %d -> %d -> %d -> %d are outside what the fused kernel takes", K0, N0, N1, N2);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const float* Wk[3] = {W0, W1, W2};
+    const float* bk[3] = {b0, b1, b2};
+    DenseW w[3];
+    for (int l = 0; l < 3; ++l) {
+        RC_TRY(w[l].alloc(N[l], K[l]));
+        pack_dense_kernel<<<blocks_for(static_cast<long long>(K[l]) * N[l]), 256, 0, st>>>(Wk[l], K[l], N[l], N[l], N[l], 0, K[l], K[l],
+                                                                                         w[l].w16.as<__nv_bfloat16>(), w[l].ld16, nullptr, 0);
+        CU_TRY(cudaMemcpyAsync(w[l].bias.p, bk[l], static_cast<size_t>(N[l]) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    const int K8 = round_up(K0, 8), D4 = round_up(N2, 4), D8 = round_up(N2, 8);
+    DevBuf a_buf, x_buf, ln_buf;
+    RC_TRY(a_buf.ensure(static_cast<size_t>(M) * K8 * 2));
+    RC_TRY(x_buf.ensure(static_cast<size_t>(M) * D4 * 4));
+    f32_to_bf16_kernel<<<blocks_for(static_cast<long long>(M) * K8), 256, 0, st>>>(A, M, K0, K0, a_buf.as<__nv_bfloat16>(), K8);
+    pad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * D4), 256, 0, st>>>(x, M, N2, N2, x_buf.as<float>(), D4);
+    MlpTailDesc td;
+    td.A = a_buf.p; td.lda = K8; td.M = M;
+    for (int l = 0; l < 3; ++l) { td.N[l] = N[l]; td.K[l] = K[l]; td.W[l] = w[l].w16.p; td.ldw[l] = w[l].ld16; td.bias[l] = w[l].bias.as<float>(); }
+    td.x = x_buf.as<float>(); td.ldx = D4; td.act = act;
+    if (ln_out) {
+        RC_TRY(ln_buf.ensure(static_cast<size_t>(M) * D8 * 2));
+        td.ln_gamma = ln_gamma; td.ln_beta = ln_beta; td.ln_eps = ln_eps; td.ln_out = ln_buf.p; td.ln_ld = D8;
+    }
+    MlpTailPlan plan;
+    int rc = mlp_tail_make_plan(&plan, td, sms);
+    if (rc) return fail(VITDET_E_INVALID, "op_mlp_tail: mlp_tail_make_plan failed: %d", rc);
+    cudaError_t te = mlp_tail_launch(plan, st);
+    if (te != cudaSuccess) return fail(VITDET_E_CUDA, "op_mlp_tail: launch failed: %s", cudaGetErrorString(te));
+    unpad_rows_f32_kernel<<<blocks_for(static_cast<long long>(M) * N2), 256, 0, st>>>(x_buf.as<float>(), M, N2, D4, x);
+    if (ln_out) bf16_rows_to_f32_kernel<<<blocks_for(static_cast<long long>(M) * N2), 256, 0, st>>>(ln_buf.as<__nv_bfloat16>(), M, N2, D8, ln_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vitdet_op_head_slots(const float* x, const float* kernel, const float* bias, float* out, int images, int tokens, int D, int S,
+                         int mode, void* stream) {
+    if (!x || !kernel || !bias || !out || images <= 0 || tokens <= 0 || D <= 0 || S <= 0) return fail(VITDET_E_INVALID, "op_head_slots: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bf = mode == VITDET_MODE_BF16;
+    const int D4 = round_up(D, 4), Tp = round_up(tokens, bf ? 8 : 4);
+    const long long M = static_cast<long long>(images) * tokens, R = static_cast<long long>(images) * S;
+    DevBuf xb, wt, ob;
+    RC_TRY(xb.ensure(static_cast<size_t>(M) * D4 * 4));
+    RC_TRY(wt.ensure(static_cast<size_t>(S) * D * 4));
+    RC_TRY(ob.ensure(static_cast<size_t>(R) * Tp * (bf ? 2 : 4)));
+    CU_TRY(cudaMemsetAsync(ob.p, 0, ob.bytes, st));
+    pad_rows_f32_kernel<<<blocks_for(M * D4), 256, 0, st>>>(x, static_cast<int>(M), D, D, xb.as<float>(), D4);
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(D) * S), 256, 0, st>>>(kernel, D, S, S, S, 0, D, D, nullptr, 0, wt.as<float>(), D);
+    CU_TRY(head_slots_launch(xb.as<float>(), D4, wt.as<float>(), bias, static_cast<int>(M), D, S, tokens, Tp, ob.p, bf ? 0 : 1, st));
+    if (bf) bf16_rows_to_f32_kernel<<<blocks_for(R * tokens), 256, 0, st>>>(ob.as<__nv_bfloat16>(), static_cast<int>(R), tokens, Tp, out);
+    else unpad_rows_f32_kernel<<<blocks_for(R * tokens), 256, 0, st>>>(ob.as<float>(), static_cast<int>(R), tokens, Tp, out);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(st));
     return 0;

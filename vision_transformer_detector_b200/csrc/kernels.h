@@ -111,7 +111,9 @@ struct AttnPlan {
     AttnDesc desc;
 };
 int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d);
-cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tcgen05 kernel (attention_tc.cu)
+cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tcgen05 kernel, one softmax thread per query row (attention_tc.cu)
+cudaError_t attn_tc8_launch(const AttnPlan& plan, cudaStream_t stream);    // tcgen05 kernel, score rows split over warp pairs (attention_tc8.cu)
+cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);   // persistent form of attention_tc.cu (attention_tcp.cu)
 cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -127,10 +129,11 @@ cudaError_t patchify_launch(const void* images, int in_u8 /*1: uint8 pixels, nor
 cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const float* beta, int M, int D,
                              float eps, void* y, int ldy, int out_f32, cudaStream_t stream);
 
-// mlp_head first stage (det.py:454-463): Dense(D -> S) on every token, stored compactly as
-// [B, T*S] so that the reference's Reshape((S,-1)) is the row-major view [B*S, T].
+// mlp_head first stage (det.py:454-463): Dense(D -> S) on every token of M / tokens images, stored as the slot matrix
+// [images*S, ldo] (ldo >= tokens; ldo == tokens is the compact [B, T*S] buffer whose row-major view IS the reference's
+// Reshape((S,-1))).
 cudaError_t head_slots_launch(const float* x, int ldx, const float* w /*[S, D] f32*/, const float* bias,
-                              int M, int D, int S, void* out, int out_f32, cudaStream_t stream);
+                              int M, int D, int S, int tokens, int ldo, void* out, int out_f32, cudaStream_t stream);
 
 // Final Dense(U -> 6) 'MLP_Head_no_Sigmoid' (det.py:489-493) fused with transform_predictions
 // (det.py:586-647) and the 0.5/0.5 thresholds (det.py:2257-2283 / 1359-1384).

@@ -184,13 +184,15 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// mlp_head first stage (det.py:454-463).  One thread per (token, slot); the output is the compact
-// row-major (M, S) matrix, whose flat buffer IS the reference's Reshape((S, -1)) result per image.
+// mlp_head first stage (det.py:454-463).  One thread per (token, slot).  The reference's Reshape((S, -1)) is a flat
+// reinterpretation of the per-image (T, S) matrix as (S, T): flat element f = t*S + s of image b lands in row b*S + f / T,
+// column f % T of the slot matrix.  With ldo == T that matrix is the compact buffer itself (out[idx]); a token count that
+// is not a multiple of the 16-byte TMA row pitch gets rows of ldo > T elements whose pad columns stay zero.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
-                  const float* __restrict__ bias, long long total, int D, int S, T* __restrict__ out) {
+                  const float* __restrict__ bias, long long total, int D, int S, int tokens, int ldo, T* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -212,7 +214,13 @@ head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         }
     }
     for (; d < D; ++d) acc = fmaf(xr[d], __ldg(wr + d), acc);
-    OutT<T>::st(out + idx, acc + __ldg(bias + s));
+    long long o = idx;
+    if (ldo != tokens) {
+        const long long per_image = static_cast<long long>(tokens) * S;
+        const long long img = idx / per_image, f = idx - img * per_image;
+        o = (img * S + f / tokens) * ldo + f % tokens;
+    }
+    OutT<T>::st(out + o, acc + __ldg(bias + s));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -421,14 +429,15 @@ cudaError_t layernorm_launch(const float* x, int ldx, const float* gamma, const 
     return ln_dispatch<32, __nv_bfloat16>(x, ldx, gamma, beta, M, D, eps, static_cast<__nv_bfloat16*>(y), ldy, stream);
 }
 
-cudaError_t head_slots_launch(const float* x, int ldx, const float* w, const float* bias, int M, int D, int S,
-                              void* out, int out_f32, cudaStream_t stream) {
+cudaError_t head_slots_launch(const float* x, int ldx, const float* w, const float* bias, int M, int D, int S, int tokens,
+                              int ldo, void* out, int out_f32, cudaStream_t stream) {
     const long long total = static_cast<long long>(M) * S;
     const int grid = static_cast<int>((total + 255) / 256);
+    if (tokens <= 0 || ldo < tokens || M % tokens) return cudaErrorInvalidValue;
     if (out_f32)
-        return launch_kernel(head_slots_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S,
+        return launch_kernel(head_slots_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S, tokens, ldo,
                              static_cast<float*>(out));
-    return launch_kernel(head_slots_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S,
+    return launch_kernel(head_slots_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S, tokens, ldo,
                          static_cast<__nv_bfloat16*>(out));
 }
 

@@ -618,6 +618,29 @@ class VisionTransformerDetector:
     def workspace_bytes(self, batch: int, compute_mode: str | None = None) -> int:
         return int(self._lib.vitdet_workspace_bytes(self._h, int(batch), self._mode(compute_mode)))
 
+    # -- run-time switches and debug taps (parity tests, A/B measurements) ---------------------------
+    def set_option(self, key: str, value: int) -> None:
+        """'fuse_ln', 'fuse_tail', 'gemm_pair' (0/1/2), 'attention' (4/8) — see include/vitdet_b200.h."""
+        _capi.check(self._lib.vitdet_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int()
+        _capi.check(self._lib.vitdet_get_option(self._h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def debug_taps(self, enable: bool = True) -> None:
+        _capi.check(self._lib.vitdet_debug_taps(self._h, 1 if enable else 0))
+
+    def debug_read(self, name: str, batch: int) -> np.ndarray:
+        """One tap of the last forward (taps enabled): 'embedded_patches', 'block_<i>' -> (batch, tokens, D) float32;
+        'head_last' -> (batch, 17, mlp_head_last_units)."""
+        if name == "head_last":
+            out = np.empty((batch, Constants.MAX_DETECT_OBJECTS_QUANTITY.value, self.config.head_units()[-1]), np.float32)
+        else:
+            out = np.empty((batch, self.config.tokens, self.config.embedding_dim), np.float32)
+        _capi.check(self._lib.vitdet_debug_read(self._h, name.encode(), _capi.np_ptr(out), out.size))
+        return out
+
     # -- measurement hooks ------------------------------------------------------------------------
     def profile_categories(self) -> list[str]:
         n = self._lib.vitdet_profile_num_categories(self._h)
