@@ -9,8 +9,12 @@
 
 A "step" = one pass of the hot path (patches -> encoder -> head -> decode) over one batch of synthetic
 images.  N = 1 runs BASELINE.json configs[1] (default config, batch 64, bf16); N > 1 runs configs[2]
-(default config, global batch 1024 sharded 1024/N per GPU, detections all-gathered with NCCL).
-Prints ONE JSON line on rank 0.
+(default config, global batch 1024 sharded 1024/N per GPU, detection records all-gathered with NCCL through
+the C ABI).  Prints ONE JSON line on rank 0.  Beside the headline the line carries: `e2e` (host buffers, copies
+inside the timed region; pinned and pageable, pipelined and synchronous), `roofline` (dominant GEMM) and
+`roofline_attention`, `variants` (configs[3] hi-res and configs[4] ViT-B width at 32 images per GPU), `fp32` (the
+fp32-accumulate mode), `multi_gpu_parity` (N > 1: gathered records == one GPU's records for the same images),
+`cpu_baseline` (N = 1).
 """
 from __future__ import annotations
 
@@ -27,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images_per_sec_fwd_decode"
 UNIT = "images/s"
-FLOP_PER_IMAGE_DEFAULT = 199.747e9      # SURVEY Appendix A (algorithmic, unpadded)
+S = 17
 
 
 def parse_args():
@@ -39,11 +43,13 @@ def parse_args():
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="override the per-GPU batch (default: 64 at N=1, 1024/N at N>1)")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--variant", default="default", choices=["default", "hires", "vitb"],
-                    help="default = BASELINE configs[1]/[2]; hires = configs[3]; vitb = configs[4]")
+                    help="headline workload: default = BASELINE configs[1]/[2]; hires = configs[3]; vitb = configs[4]")
     ap.add_argument("--chunk", type=int, default=0, help="encoder micro-batch (images); 0 = library default")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the hi-res / ViT-B-width / fp32 side measurements")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the gathered-records == single-GPU check")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-category time table to stderr")
     return ap.parse_args()
 
@@ -69,7 +75,6 @@ def flops_per_image(cfg) -> float:
         mlp += 2.0 * T * fan * u
         fan = u
     f += L * (3 * 2.0 * T * D * H * d + 2 * 2.0 * H * T * T * d + 2.0 * T * H * d * D + mlp)
-    S = 17
     f += 2.0 * T * D * S
     fan = T
     for u in cfg.head_units():
@@ -77,6 +82,19 @@ def flops_per_image(cfg) -> float:
         fan = u
     f += 2.0 * S * fan * 6
     return f
+
+
+def category_flops_per_image(cfg) -> dict:
+    """Algorithmic FLOPs per image of the kernel categories the engine times (whole model, all blocks)."""
+    T, P, D = cfg.tokens, cfg.patch_dim, cfg.embedding_dim
+    H, d, L = cfg.encoder_num_heads, cfg.encoder_key_dim, cfg.encoder_repeat_times
+    out = {"gemm_linear_projection": 2.0 * T * P * D, "gemm_qkv": L * 3 * 2.0 * T * D * H * d,
+           "attention": L * 4.0 * H * T * T * d, "gemm_attention_output": L * 2.0 * T * H * d * D}
+    fan = D
+    for j, u in enumerate(cfg.encoder_mlp_units()):
+        out[f"gemm_mlp_{j + 1}"] = L * 2.0 * T * fan * u
+        fan = u
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -99,6 +117,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -201,164 +220,264 @@ def bind_to_gpu_numa_node(torch, local_rank: int):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import vision_transformer_detector_b200 as vd
+        from vision_transformer_detector_b200 import parallel
+        self.args, self.torch, self.dist, self.vd, self.parallel = args, torch, dist, vd, parallel
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa_cpus = bind_to_gpu_numa_node(torch, self.local_rank) if self.world > 1 else None
+        self.gather = None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL prints a version banner on STDOUT when a communicator is created: send fd 1 to stderr until both
+            # communicators (torch's for barriers / reductions, the library's for the record gather) exist, so that
+            # stdout carries exactly one JSON line
+            sys.stdout.flush()
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+                self.gather = parallel.RecordGather(self.dev)
+                self.gather.all_gather(torch.zeros((S, parallel.RECORD_WIDTH), device=self.dev))
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make(self, variant: str, mode: str, B: int):
+        vd, torch = self.vd, self.torch
+        cfg, desc = variant_config(vd, variant)
+        model = vd.VisionTransformerDetector(cfg, seed=None, compute_mode=mode)
+        model.set_weights(vd.random_weights(cfg, seed=1, spread=True))
+        if self.args.chunk:
+            model.set_chunk(self.args.chunk)
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(1234 + self.rank)
+        x = torch.rand((B, *cfg.input_shape), generator=g, device=self.dev, dtype=torch.float32) * 2 - 1
+        return model, cfg, desc, x
+
+    def step_fn(self, model, x, img_size):
+        if self.world > 1:
+            gather = self.gather
+
+            def step():
+                # the path's only exchange: the packed records the head-tail kernel wrote, all-gathered by the C ABI
+                return gather.all_gather(model.detect(x, image_size=img_size, packed=True).packed)
+        else:
+            def step():
+                return model.detect(x, image_size=img_size)
+        return step
+
+    def time_device(self, model, step, steps, warmup, categories):
+        """W untimed steps, then K steps between CUDA events on the launching stream, bracketed by barrier + synchronize;
+        max over ranks.  `categories` are timed by the engine's own events (None = none)."""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            step()
+        self.barrier()
+        model.launch_count(reset=True)
+        model.profile_read(reset=True)
+        model.profile_enable(categories)
+        sampler = ClockSampler(self.local_rank).start() if self.rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        self.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms_total = self.max_over_ranks(ev0.elapsed_time(ev1))
+        launches = model.launch_count(reset=True)      # kernels of this library only (NCCL not counted)
+        prof = model.profile_read(reset=True)
+        model.profile_enable(None)
+        return ms_total, launches, prof, clocks
+
+    def time_host(self, model, x_np, img_size, steps, pipelined: bool, bytes_per_elem: int, cfg, B):
+        """The reference-facing call with HOST buffers: H2D copy of every step's images, forward + decode, D2H read of
+        the records, all inside the timed region.  pipelined: two submissions in flight (submit / collect), so the copy of
+        step i+1 overlaps the compute of step i; otherwise one synchronous detect() per step."""
+        import numpy as np
+        torch = self.torch
+        world, gather = self.world, self.gather
+
+        def finish(rec):
+            if world > 1:
+                gather.all_gather(torch.from_numpy(rec.packed).to(self.dev, non_blocking=False))
+
+        def run(n):
+            if pipelined:
+                t = model.submit(x_np, image_size=img_size, packed=world > 1)
+                for _ in range(n - 1):
+                    t2 = model.submit(x_np, image_size=img_size, packed=world > 1)
+                    finish(model.collect(t))
+                    t = t2
+                finish(model.collect(t))
+            else:
+                for _ in range(n):
+                    finish(model.detect(x_np, image_size=img_size, packed=world > 1))
+
+        run(2)
+        self.barrier()
+        t0 = time.perf_counter()
+        run(steps)
+        self.barrier()
+        wall = self.max_over_ranks(time.perf_counter() - t0)
+        return {"value": world * B * steps / wall, "unit": UNIT,
+                "h2d_bytes_per_step": int(world * B * np.prod(cfg.input_shape) * bytes_per_elem),
+                "d2h_bytes_per_step": int(world * B * S * (24 + 24 + 4 + 4 + 16 + 1 + (52 if world > 1 else 0))),
+                "timing": "host wall clock around K steps (the call is synchronous at collect), max over ranks",
+                "pipelined": pipelined}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1590.0, "hbm_gbs": 6553.0, "source": "fallback (B200_PROFILING.md)"}
+    if os.path.exists(path):
+        pk = json.load(open(path))
+        out = {"bf16_tflops": float(pk.get("bf16_tflops", 1590.0)), "bf16_tflops_sustained": float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))),
+               "hbm_gbs": float(pk.get("hbm_gbs", 6553.0)), "source": "MEASURED_PEAKS.json"}
+    return out
+
+
+def gemm_roofline(cfg, B, steps, prof, name, ms_step_total, pk):
+    """Tensor-pipe roofline of one Dense category from the engine's live CUDA-event timing of exactly those launches."""
+    if name not in prof:
+        return None
+    ms_k, n_k = prof[name]
+    j = int(name.rsplit("_", 1)[1]) - 1
+    units = cfg.encoder_mlp_units()
+    K_ = cfg.embedding_dim if j == 0 else units[j - 1]
+    N_ = units[j]
+    rows_total = B * cfg.tokens * steps * cfg.encoder_repeat_times
+    achieved = 2.0 * rows_total * K_ * N_ / (ms_k * 1e-3) / 1e12
+    rows_launch = rows_total / n_k
+    r = {"bound": "tensor", "kernel": f"{'gemm_tc2_kernel (CTA pair)' if K_ >= 512 and N_ >= 128 else 'gemm_tc_kernel'}[{name}: K={K_} -> N={N_}, bias+Mish epilogue]",
+         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+         "peak_source": f"measured sustained ({pk['source']}): the kernel is timed inside a long step", "peak_burst": pk["bf16_tflops"],
+         "frac_of_burst": achieved / pk["bf16_tflops"], "launches": n_k, "avg_launch_ms": ms_k / n_k,
+         "share_of_step": ms_k / ms_step_total, "algorithmic_flop_per_launch": 2.0 * rows_launch * K_ * N_,
+         "algorithmic_bytes": 2.0 * (rows_launch * (K_ + N_) + K_ * N_), "traffic": None}
+    return r
+
+
+def attention_roofline(cfg, B, steps, prof, ms_step_total, pk, clocks):
+    """The attention kernel against BOTH units it could be bound by: the tensor pipe (4 H T^2 d FLOP) and the SFU
+    (one ex2 per score, 16 per clock and SM at the SM clock sampled during the run)."""
+    if "attention" not in prof:
+        return None
+    ms_k, n_k = prof["attention"]
+    H, d, T, L = cfg.encoder_num_heads, cfg.encoder_key_dim, cfg.tokens, cfg.encoder_repeat_times
+    images = B * steps
+    flops = 4.0 * H * T * T * d * L * images
+    ex2 = 1.0 * H * T * T * L * images
+    tf = flops / (ms_k * 1e-3) / 1e12
+    out = {"kernel": "attn_tc8p_kernel / attn_tcp_kernel (persistent flash attention, S/P/O in TMEM)", "launches": n_k, "avg_launch_ms": ms_k / n_k,
+           "share_of_step": ms_k / ms_step_total, "tensor": {"achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"]},
+           "note": "at head_dim 40 one score costs 160 tensor FLOP and one SFU ex2: the SFU (16/clk/SM) needs ~2.3x the tensor pipe's time, so it is the binding unit"}
+    mhz = (clocks or {}).get("sm_mhz")
+    if mhz:
+        sfu_peak = 148 * 16 * mhz * 1e6
+        out["sfu"] = {"achieved": ex2 / (ms_k * 1e-3) / 1e12, "peak": sfu_peak / 1e12, "unit": "T ex2/s", "frac": ex2 / (ms_k * 1e-3) / sfu_peak,
+                      "sm_mhz": mhz}
+    return out
+
+
 def run_ours(args):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    import vision_transformer_detector_b200 as vd
-    from vision_transformer_detector_b200 import parallel
+    b = Bench(args)
+    torch, vd, parallel, world, rank = b.torch, b.vd, b.parallel, b.world, b.rank
+    assert parallel.RECORD_WIDTH == 13
+    pk = peaks()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa_cpus = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints a version banner on STDOUT when the communicator is created: send fd 1 to stderr until the
-        # first collective has run, so that stdout carries exactly one JSON line
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-
-    cfg, desc = variant_config(vd, args.variant)
     if args.batch_per_gpu:
         B = args.batch_per_gpu
     elif args.variant == "default":
         B = 64 if world == 1 else 1024 // world
     else:
         B = 32
-    S = 17
-    model = vd.VisionTransformerDetector(cfg, seed=None, compute_mode=args.mode)
-    model.set_weights(vd.random_weights(cfg, seed=1, spread=True))
-    if args.chunk:
-        model.set_chunk(args.chunk)
-
-    # synthetic inputs: per-rank seed, resident in HBM for `value`, in pinned host memory for `e2e`
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    x_dev = torch.rand((B, *cfg.input_shape), generator=g, device=dev, dtype=torch.float32) * 2 - 1
+    model, cfg, desc, x_dev = b.make(args.variant, args.mode, B)
     img_size = cfg.input_shape[:2]
-    rec_bytes = S * (24 + 4 + 4 + 1 + 16)      # decoded, class_id, class_conf, keep, corners per image
-    assert parallel.RECORD_WIDTH == 13
-
-    def step():
-        rec = model.detect(x_dev, image_size=img_size)
-        if world > 1:
-            # the path's only exchange: fixed-size detection records of every rank, all-gathered (NCCL)
-            return parallel.all_gather_records(parallel.pack_records(rec))
-        return rec
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
+    step = b.step_fn(model, x_dev, img_size)
     names = model.profile_categories()
     dominant = "gemm_mlp_2" if "gemm_mlp_2" in names else names[-1]
-    model.launch_count(reset=True)
-    model.profile_read(reset=True)
-    model.profile_enable([dominant])
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = ev0.elapsed_time(ev1)
-    launches = model.launch_count(reset=True)      # kernels of this library only (NCCL / torch packing not counted)
-    prof = model.profile_read(reset=True)
-    model.profile_enable(None)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, launches, prof, clocks = b.time_device(model, step, args.steps, args.warmup, [dominant, "attention"])
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+    roofline = gemm_roofline(cfg, B, args.steps, prof, dominant, ms_total, pk) if args.mode == "bf16" else None
+    if roofline is not None:
+        tpath = os.path.join(ROOT, "profiles", "gemm_mlp_2_traffic.json")
+        if os.path.exists(tpath) and args.variant == "default":
+            tj = json.load(open(tpath))
+            from vision_transformer_detector_b200 import build as _b
+            # dram bytes of one launch from the committed `ncu --set full` capture; only quoted for the source tree it was
+            # taken on (scripts/gpu_ncu_traffic.sh stamps the capture with the csrc hash) and the same rows per launch
+            if tj.get("csrc_hash") == _b._source_hash() and tj.get("rows_per_launch") == roofline["algorithmic_flop_per_launch"] / (2.0 * 3584 * 1792):
+                roofline["traffic"] = tj.get("traffic_bytes_per_launch")
+            else:
+                roofline["traffic_note"] = "profiles/gemm_mlp_2_traffic.json was captured on another source tree / launch size: not quoted"
+    roof_attn = attention_roofline(cfg, B, args.steps, prof, ms_total, pk, clocks) if args.mode == "bf16" else None
+
+    # ---- multi-GPU parity: the gathered records of the first images of every rank == rank 0's own run on those images ----
+    parity = None
+    if world > 1 and not args.no_verify:
+        nv = min(8, B)
+        mine = x_dev[:nv].contiguous()
+        allx = torch.empty((world * nv, *cfg.input_shape), dtype=torch.float32, device=b.dev)
+        b.dist.all_gather_into_tensor(allx, mine)
+        gathered = b.gather.all_gather(model.detect(mine, image_size=img_size, packed=True).packed)
+        single = model.detect(allx, image_size=img_size, packed=True).packed
+        ok = torch.tensor([1.0 if torch.equal(gathered, single) else 0.0], device=b.dev)
+        b.dist.all_reduce(ok, op=b.dist.ReduceOp.MIN)
+        parity = bool(ok.item() == 1.0)
+        del allx, gathered, single
 
     # ---- e2e: the reference-facing call with HOST buffers (H2D + forward + decode + D2H inside) ----
-    e2e = None
-    e2e_u8 = None
+    e2e = {}
     if not args.no_e2e:
-        def time_host_path(x_np, bytes_per_elem):
-            for _ in range(2):
-                model.detect(x_np, image_size=img_size)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                rec = model.detect(x_np, image_size=img_size)     # vitdet_predict_host[_u8]: synchronous, returns numpy records
-                if world > 1:
-                    parallel.all_gather_records(torch.from_numpy(parallel.pack_records(rec)).to(dev))
-            e1.record()
-            barrier()
-            wall = time.perf_counter() - t0
-            tt = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return {"value": world * B * args.steps / float(tt.item()), "unit": UNIT,
-                    "h2d_bytes_per_step": int(world * B * np.prod(cfg.input_shape) * bytes_per_elem),
-                    "d2h_bytes_per_step": int(world * B * (S * 24 + rec_bytes)),
-                    "host_affinity": (f"{len(numa_cpus)} cpus local to the GPU" if numa_cpus else "unbound")}
-
-        x_host = torch.empty((B, *cfg.input_shape), dtype=torch.float32, pin_memory=True)
-        x_host.copy_(x_dev)
-        e2e = time_host_path(x_host.numpy(), 4)
+        x_pin = torch.empty((B, *cfg.input_shape), dtype=torch.float32, pin_memory=True)
+        x_pin.copy_(x_dev)
+        e2e["e2e"] = b.time_host(model, x_pin.numpy(), img_size, args.steps, True, 4, cfg, B)
+        e2e["e2e"]["host_buffer"] = "page-locked"
+        e2e["e2e_sync"] = b.time_host(model, x_pin.numpy(), img_size, args.steps, False, 4, cfg, B)
+        x_page = np.array(x_pin.numpy(), copy=True)          # an ordinary numpy array, as a reference caller would pass
+        del x_pin
+        e2e["e2e_pageable"] = b.time_host(model, x_page, img_size, args.steps, True, 4, cfg, B)
+        e2e["e2e_pageable"]["host_buffer"] = "pageable numpy array, staged through pinned memory by the library's staging threads"
+        e2e["e2e_pageable_sync"] = b.time_host(model, x_page, img_size, args.steps, False, 4, cfg, B)
+        del x_page
         # the same call fed with the uint8 pixels the reference's input pipeline starts from
         # (vision_transformer_utilities.py:446-447: x / 127.5 - 1, here inside the patch kernel); extra, not the headline
-        u_host = torch.empty((B, *cfg.input_shape), dtype=torch.uint8, pin_memory=True)
-        u_host.copy_(((x_dev + 1) * 127.5).round().clamp(0, 255).to(torch.uint8))
-        e2e_u8 = time_host_path(u_host.numpy(), 1)
-        e2e_u8["input"] = "uint8 NHWC pixels, normalised on the device"
-        del x_host, u_host
-
-    # ---- roofline of the dominant kernel (the 3584 -> 1792 MLP GEMM in the default config) ----
-    roofline = None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak_tf, peak_src, pk_burst = 1590.0, "fallback (B200_PROFILING.md)", 1590.0
-    if os.path.exists(peaks_path):
-        pk = json.load(open(peaks_path))
-        # the kernel is timed inside a long step -> sustained figure
-        peak_tf, peak_src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured sustained (MEASURED_PEAKS.json)"
-        pk_burst = float(pk.get("bf16_tflops", peak_tf))
-    if dominant in prof and args.mode == "bf16":
-        ms_k, n_k = prof[dominant]
-        units = cfg.encoder_mlp_units()
-        K_, N_ = (units[0], units[1]) if len(units) > 1 else (cfg.embedding_dim, units[0])
-        chunk = args.chunk or 64
-        rows_total = B * cfg.tokens * args.steps * cfg.encoder_repeat_times     # rows pushed through this layer in the timed region
-        flops_total = 2.0 * rows_total * K_ * N_
-        achieved = flops_total / (ms_k * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "gemm_mlp_2_traffic.json")
-        if os.path.exists(tpath) and args.variant == "default" and B == 64:
-            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")      # from the committed ncu --set full capture
-        roofline = {"bound": "tensor", "kernel": f"{'gemm_tc2_kernel (CTA pair)' if K_ >= 512 and N_ >= 128 else 'gemm_tc_kernel'}[{dominant}: K={K_} -> N={N_}, bias+Mish epilogue]",
-                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src, "peak_burst": pk_burst, "frac_of_burst": (achieved / pk_burst if pk_burst else None), "launches": n_k, "avg_launch_ms": ms_k / n_k,
-                    "share_of_step": ms_k / (ms_step * args.steps), "traffic": traffic,
-                    "algorithmic_bytes": 2.0 * (B * cfg.tokens * (K_ + N_) + K_ * N_)}
+        u_pin = torch.empty((B, *cfg.input_shape), dtype=torch.uint8, pin_memory=True)
+        u_pin.copy_(((x_dev + 1) * 127.5).round().clamp(0, 255).to(torch.uint8))
+        e2e["e2e_uint8"] = b.time_host(model, u_pin.numpy(), img_size, args.steps, True, 1, cfg, B)
+        e2e["e2e_uint8"]["input"] = "uint8 NHWC pixels, normalised on the device"
+        del u_pin
+        for v in e2e.values():
+            v["host_affinity"] = f"{len(b.numa_cpus)} cpus local to the GPU" if b.numa_cpus else "unbound"
 
     breakdown = None
     if args.breakdown:
@@ -369,31 +488,81 @@ def run_ours(args):
         breakdown = {k: {"ms_per_step": v[0] / 2, "launches_per_step": v[1] // 2} for k, v in model.profile_read().items()}
         model.profile_enable(None)
 
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        weights = {w.name[:-2]: w.numpy() for w in model.weights}
+        v, ms, cores = cpu_forward_decode_rate(vd, cfg, weights, args.cpu_sample, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} images per step x 3 steps of the same workload (float32 oracle port of the reference on torch CPU; TF 2.9 not installable)"}
+    model.close()
+    del model, x_dev
+    torch.cuda.empty_cache()
+
+    # ---- side measurements: the other BASELINE.json configurations and the fp32-accumulate mode ----
+    variants, fp32 = None, None
+    if not args.no_variants and args.variant == "default" and args.mode == "bf16":
+        variants = {}
+        for vname in ("hires", "vitb"):
+            vb = 32                                          # configs[3]: 32 per GPU; configs[4]: 256 across 8 = 32 per GPU
+            m2, c2, d2, x2 = b.make(vname, "bf16", vb)
+            st2 = b.step_fn(m2, x2, c2.input_shape[:2])
+            cats = m2.profile_categories()
+            vsteps = max(3, min(args.steps, 6))
+            ms2, l2, prof2, clk2 = b.time_device(m2, st2, vsteps, 3, [c for c in cats if c.startswith("gemm_") or c == "attention"])
+            top = max(prof2.items(), key=lambda kv: kv[1][0])[0] if prof2 else None
+            entry = {"workload": f"{d2}; batch {vb}/GPU x {world} GPU(s)", "value": world * vb * vsteps / (ms2 * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms2 / vsteps, "steps": vsteps, "gpu_launches": int(l2), "clocks": clk2,
+                     "flop_per_image": flops_per_image(c2), "model_tflops": world * vb * vsteps / (ms2 * 1e-3) * flops_per_image(c2) / 1e12,
+                     "dominant_kernel": top}
+            if top == "attention":
+                entry["roofline"] = attention_roofline(c2, vb, vsteps, prof2, ms2, pk, clk2)
+            elif top and top.startswith("gemm_mlp_"):
+                entry["roofline"] = gemm_roofline(c2, vb, vsteps, prof2, top, ms2, pk)
+            entry["category_ms_per_step"] = {k: v[0] / vsteps for k, v in sorted(prof2.items(), key=lambda kv: -kv[1][0])}
+            entry["roofline_attention"] = attention_roofline(c2, vb, vsteps, prof2, ms2, pk, clk2)
+            if not args.no_e2e:
+                xp = torch.empty((vb, *c2.input_shape), dtype=torch.float32, pin_memory=True)
+                xp.copy_(x2)
+                entry["e2e"] = b.time_host(m2, xp.numpy(), c2.input_shape[:2], vsteps, True, 4, c2, vb)
+                del xp
+            variants[vname] = entry
+            m2.close()
+            del m2, x2
+            torch.cuda.empty_cache()
+        fb = 64 if world == 1 else min(64, 1024 // world)
+        m3, c3, d3, x3 = b.make("default", "fp32", fb)
+        st3 = b.step_fn(m3, x3, c3.input_shape[:2])
+        ms3, l3, _, clk3 = b.time_device(m3, st3, 3, 3, None)
+        fp32 = {"workload": f"{d3}; batch {fb}/GPU x {world} GPU(s); fp32-accumulate mode (north_star tolerance 1e-3)",
+                "value": world * fb * 3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / 3, "steps": 3, "gpu_launches": int(l3), "clocks": clk3}
+        m3.close()
+        del m3, x3
+
     if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            weights = {w.name[:-2]: w.numpy() for w in model.weights}
-            v, ms, cores = cpu_forward_decode_rate(vd, cfg, weights, args.cpu_sample, 3, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_sample} images per step x 3 steps of the same workload (float32 oracle port of the reference on torch CPU; TF 2.9 not installable)"}
         fpi = flops_per_image(cfg)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (world == 1 or args.batch_per_gpu) else "strong",
             "vs_baseline": None, "dtype": args.mode, "data": "synthetic U(-1,1) images, random-init weights (Keras initialisers, spread set)",
             "config": {"workload": f"{desc}; batch {B}/GPU x {world} GPU(s); forward + fused decode"
-                                   + ("; NCCL all-gather of detection records" if world > 1 else ""),
+                                   + ("; NCCL all-gather of detection records (vitdet_gather_detections)" if world > 1 else ""),
                        "global_batch": B * world, "tokens": cfg.tokens, "flop_per_image": fpi,
                        "l2_policy": "inputs and activations (>= 283 MB per step) exceed the 126 MB L2; no flush between steps"},
             "model_tflops": value * fpi / 1e12,
-            "e2e": e2e, "e2e_uint8": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e.get("e2e"), "e2e_sync": e2e.get("e2e_sync"), "e2e_pageable": e2e.get("e2e_pageable"),
+            "e2e_pageable_sync": e2e.get("e2e_pageable_sync"), "e2e_uint8": e2e.get("e2e_uint8"),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_attention": roof_attn,
+            "cpu_baseline": cpu, "variants": variants, "fp32": fp32,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if breakdown:
             line["breakdown"] = breakdown
             print(json.dumps(breakdown, indent=1), file=sys.stderr)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        b.gather.close()
+        b.dist.destroy_process_group()
 
 
 def main():

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VITDET_ABI_VERSION 1
+#define VITDET_ABI_VERSION 2
 
 enum {
     VITDET_OK = 0,
@@ -158,13 +158,17 @@ typedef struct vitdet_decode_params {
  *   class_id  [R]   i32  round-half-even(class)                              (det.py:1366, :2271)
  *   class_conf[R]   f32  (0.5 - |class - id|) / 0.5                           (det.py:1376, :2279)
  *   keep      [R]   u8   1 iff both scores pass their thresholds
- *   corners   [R,4] i32  x0,y0,x1,y1: int() truncation then clip to the image (det.py:2300-2325) */
+ *   corners   [R,4] i32  x0,y0,x1,y1: int() truncation then clip to the image (det.py:2300-2325)
+ *   packed    [R,13] f32 the same record as one row: decoded[6] | class id | class confidence | keep | corners[4]
+ *                        (integers are exact in float32) — what vitdet_gather_detections exchanges between GPUs */
+#define VITDET_RECORD_FLOATS 13
 typedef struct vitdet_detections {
     float* decoded;
     int32_t* class_id;
     float* class_conf;
     uint8_t* keep;
     int32_t* corners;
+    float* packed;
 } vitdet_detections;
 
 /* Replaces transform_predictions (det.py:586-647) + the threshold rule on R = B*num_slots rows of
@@ -208,6 +212,19 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
                         const vitdet_decode_params* params, float* logits_host,
                         const vitdet_detections* out_host, void* stream);
 
+/* ---- multi-GPU: the path's only exchange ----
+ * Images are independent, so the batch is sharded over one process per GPU with no collective inside the forward; the
+ * fixed-size detection records (vitdet_detections.packed, 13 floats per slot) of every rank are then all-gathered in
+ * rank order with NCCL over NVLink.  `nccl_comm` is the caller's ncclComm_t (passed as void*: this header needs no
+ * nccl.h); the library binds to the libnccl.so.2 that is already loaded in the process (or VITDET_NCCL_LIB).
+ * packed_local_dev: [rows_local, 13] on this rank; packed_all_dev: [world * rows_local, 13]; asynchronous on `stream`. */
+int vitdet_gather_detections(void* nccl_comm, const float* packed_local_dev, int rows_local, float* packed_all_dev, void* stream);
+/* For callers without a communicator of their own: rank 0 obtains a 128-byte id and distributes it by any means (the
+ * Python side broadcasts it through torch.distributed); every rank then creates the communicator on its current device. */
+int vitdet_nccl_unique_id(char id_out[128]);
+int vitdet_nccl_comm_create(const char id[128], int rank, int world, void** nccl_comm_out);
+int vitdet_nccl_comm_destroy(void* nccl_comm);
+
 /* ---- uint8 input ("next" row N4, fused with the patch kernel) ----
  * The reference's input pipeline turns uint8 pixels into the model's float32 input with x / 127.5 - 1
  * (vision_transformer_utilities.py:446-447).  These two entry points take the uint8 pixels themselves — NHWC
@@ -221,6 +238,17 @@ int vitdet_forward_u8(vitdet_handle* h, const uint8_t* images_dev, int B, float*
 int vitdet_predict_host_u8(vitdet_handle* h, const uint8_t* images_host, int B, int mode,
                            const vitdet_decode_params* params, float* logits_host,
                            const vitdet_detections* out_host, void* stream);
+
+/* Asynchronous form of the two host calls above, for callers that stream batches: vitdet_submit_host stages and copies
+ * the images (page-locked caller buffers are read directly; ordinary pageable ones are staged through pinned memory by
+ * a few threads, overlapped with the copy), enqueues forward + decode + the read-back of the record block on `stream`
+ * and returns a ticket; vitdet_collect waits for that ticket and fills the HOST outputs.  Up to two submissions may be
+ * in flight per handle: the host->device copy of submission i+1 then overlaps the compute of submission i.
+ * images_host must stay valid until the submit call returns (pageable) / until the ticket is collected (page-locked).
+ * want_packed: also produce vitdet_detections.packed.  vitdet_predict_host[_u8] = submit + collect. */
+int vitdet_submit_host(vitdet_handle* h, const void* images_host, int images_are_uint8, int B, int mode,
+                       const vitdet_decode_params* params, int want_packed, void* stream, int* ticket);
+int vitdet_collect(vitdet_handle* h, int ticket, float* logits_host, const vitdet_detections* out_host);
 
 /* ---- evaluation metric ("next" row N2): MeanAveragePrecision of the reference (det.py:1268-2060) ----
  * The COCO-style AP of the reference: mean over the IoU thresholds tf.linspace(0.5, 0.95, 10) of the mean, over the

@@ -62,13 +62,14 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/vitdet_b200.h but not exported"
     assert declared == set(_capi.SYMBOLS), "ctypes table and header disagree"
-    assert _capi.load().vitdet_abi_version() == 1
+    assert _capi.load().vitdet_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_capi.Config) == 15 * 4
     assert ctypes.sizeof(_capi.DecodeParams) == 8 * 4
-    assert ctypes.sizeof(_capi.Detections) == 5 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_capi.Detections) == 6 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_capi.DenseEx) == 56
     c = _capi.default_config()
     assert (c.image_h, c.image_w, c.patch_size, c.embedding_dim, c.num_heads, c.key_dim) == (608, 608, 17, 28, 8, 40)
     assert (c.mlp_quantities, c.repeat_times, c.head_last_units, c.head_dense_layers, c.head_block_repeats) == (8, 8, 136, 7, 1)

@@ -63,7 +63,7 @@ class Detections(C.Structure):
     """struct vitdet_detections (device or host pointers depending on the call)."""
     _fields_ = [
         ("decoded", C.c_void_p), ("class_id", C.c_void_p), ("class_conf", C.c_void_p),
-        ("keep", C.c_void_p), ("corners", C.c_void_p),
+        ("keep", C.c_void_p), ("corners", C.c_void_p), ("packed", C.c_void_p),
     ]
 
 
@@ -117,6 +117,12 @@ SYMBOLS = {
     "vitdet_op_dense_ex": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DenseEx), _P]),
     "vitdet_op_mlp_tail": (C.c_int, [_P] * 8 + [_P, _P, C.c_float, _P] + [C.c_int] * 6 + [_P]),
     "vitdet_op_head_slots": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vitdet_submit_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(DecodeParams), C.c_int, _P, C.POINTER(C.c_int)]),
+    "vitdet_collect": (C.c_int, [_P, C.c_int, _P, C.POINTER(Detections)]),
+    "vitdet_gather_detections": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "vitdet_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "vitdet_nccl_comm_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vitdet_nccl_comm_destroy": (C.c_int, [_P]),
     "vitdet_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "vitdet_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int)]),
     "vitdet_debug_taps": (C.c_int, [_P, C.c_int]),
@@ -145,8 +151,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vitdet_abi_version() != 1:
-        raise ImportError(f"{path}: ABI version {lib.vitdet_abi_version()} != 1")
+    if lib.vitdet_abi_version() != 2:
+        raise ImportError(f"{path}: ABI version {lib.vitdet_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -16,7 +16,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libvitdet_b200.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libvitdet_b200.stamp")
 
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention.cu", "attention_tc.cu", "attention_tc8.cu", "attention_tcp.cu", "mlp_tail.cu", "rowops.cu", "metric.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention.cu", "attention_tc.cu", "attention_tc8.cu", "attention_tcp.cu", "attention_sw.cu", "attention_pp.cu", "attention_tc8p.cu", "mlp_tail.cu", "rowops.cu", "metric.cu", "gather.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -79,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         msg = "\n".join(f"--- {s} ---\n{o}" for s, o in failed)
         raise RuntimeError(f"nvcc failed:\n{msg}")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

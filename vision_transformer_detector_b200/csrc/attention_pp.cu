@@ -1,18 +1,23 @@
-// Multi-head self-attention core, PERSISTENT form: softmax(q k^T / sqrt(d)) v per (image, head) on tcgen05 without
-// materialising the (B, H, T, T) score tensor of keras.layers.MultiHeadAttention (reference det.py:364-369).
+// Multi-head self-attention core: persistent PING-PONG kernel — softmax(q k^T / sqrt(d)) v per (image, head) on tcgen05
+// without materialising the (B, H, T, T) score tensor of keras.layers.MultiHeadAttention (reference det.py:364-369).
 //
-// Same per-tile machinery as attention_tc.cu (one softmax thread per query row, S | P | O in 256 TMEM columns, P fed to
-// the PV product from tensor memory, lazy rescale, two CTAs per SM), but a CTA no longer lives for one 128-query work
-// item: the per-instruction samples of that kernel (profiles/r02_attention_analysis.md) put a fifth of the softmax warps'
-// time into the start and the end of a CTA — TMEM allocation + barrier set-up, the first Q / K tiles' flight from L2,
-// the first QK^T, and the final drain — during which the SFU, the binding unit, idles.  Here the grid is 2 x #SM CTAs
-// and every role loops over a FLAT sequence of key tiles g = 0 .. items * tiles-per-item - 1:
-//   warp 4  TMA producer: Q of item i+1 into the second Q buffer while item i computes; K tiles through a 2-slot ring and
-//           V tiles through a 3-slot ring (K(j) is free once QK^T(j) has run, V(j) only after PV(j) a tile later)
-//   warp 5  MMA issuer: QK^T(g + 1) is issued as soon as the softmax warps hold S(g) in registers — also across an item
-//           boundary, so the first scores of the next item are ready before the current item's last P is written
-//   warps 0..3  softmax; the last tile of an item is followed by O / l -> ctx and a reset of the running statistics
-// TMEM allocation, barrier initialisation and tensor-map prefetch happen once per CTA.
+// Why ping-pong.  The binding unit is the SFU (one ex2 per score, 16 per clock and SM).  ptxas already paces a softmax
+// warp at exactly that rate inside its exponential phase (MUFU stall counts add up to 16 clocks per pair of scores), so
+// ONE warp per SM sub-partition could keep the SFU busy — yet the earlier kernels (attention_tc.cu, attention_tcp.cu:
+// two CTAs per SM, i.e. two softmax warps per sub-partition) sit at 66 % SFU activity whatever else is changed
+// (persistence, more warps, exponentials moved to the FMA pipe: profiles/r02_attention_analysis.md).  The cause is a
+// convoy: the two warps of a sub-partition share the SFU fairly, so two overlapping exponential phases (1024 SFU clocks
+// each) end together after 2048 clocks, after which BOTH warps do their ~1000 clocks of non-SFU work (P to TMEM, barrier
+// hand-offs, next S from TMEM, row maximum) at the same time with the SFU idle: 2048 / (2048 + 1000) = 67 %.
+// Here the two work streams live in ONE CTA per SM ("lanes" 0 and 1: own Q / K / V rings, own barriers, own half of the
+// 512 TMEM columns, own TMA-producer and MMA-issuer warps) and the softmax warps w (lane 0) and w + 4 (lane 1) of a
+// sub-partition hand the SFU to each other through a pair of 64-thread named barriers: a warp waits for its turn before
+// its exponential phase and passes the turn on after it, so one lane's non-SFU work always runs under the other lane's
+// exponentials.
+//   warps 0..3   softmax, lane 0 (warp = TMEM lane quadrant)      warps 4..7   softmax, lane 1
+//   warps 8, 9   TMA producers of lane 0 / 1                       warps 10, 11 MMA issuers of lane 0 / 1 (warp 10 owns TMEM)
+// Per lane the tile loop is the flat persistent one of attention_tcp.cu: Q double-buffered, K and V tiles in 2-slot rings,
+// QK^T(g+1) issued as soon as S(g) is in registers, also across work-item boundaries.
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -26,20 +31,22 @@ namespace {
 constexpr int kQ = 128;            // queries per work item (UMMA M)
 constexpr int kKV = 128;           // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kHP = 64;            // head pitch in shared memory (one 128-byte swizzle row of bf16)
-constexpr int kKSlots = 2, kVSlots = 3, kQSlots = 2;
-constexpr int kThreads = 192;
-constexpr int kProducerWarp = 4, kMmaWarp = 5;      // highest warp ids: favoured by the arbiter
+constexpr int kKSlots = 2, kVSlots = 2, kQSlots = 2;      // per lane: 96 KB, 192 KB for the CTA
+constexpr int kLanes = 2;
+constexpr int kThreads = 32 * (4 * kLanes + 2 * kLanes);
+constexpr int kProducerWarp0 = 4 * kLanes, kMmaWarp0 = 4 * kLanes + kLanes;      // producers 8, 9; MMA issuers 10, 11
 constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
 constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one K tile or one V tile = two TMA boxes of 64 rows
 constexpr int kBoxBytes = 64 * kHP * 2;
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 256;          // per lane; the CTA allocates 512
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;   // S [0,128) f32 | P [128,192) bf16x2 | O [192,256) f32
 constexpr float kRescaleThreshold = 8.f;      // log2 units: P stays <= 2^8 between rescales
 constexpr int kRing = kKSlots + kVSlots + kQSlots;
-constexpr int kNumBars = 2 * kRing + 4;
+constexpr int kNumBars = 2 * kRing + 4;   // per lane
 constexpr int kDefaultPoly = 0;
+constexpr int kLaneSmem = kQSlots * kQBytes + (kKSlots + kVSlots) * kTileBytes;
 
-struct AttnTcpArgs {
+struct AttnPpArgs {
     __nv_bfloat16* ctx;
     int ldo;
     int T, H;
@@ -80,7 +87,12 @@ __device__ __forceinline__ void exp2_pair_poly(uint64_t t2, float& e0, float& e1
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
-struct TileBars { uint32_t s_free, pv_done, p_full; };
+struct TileBars { uint32_t s_free, pv_done, p_full; int turn_mine, turn_other; };
+
+// The SFU hand-off between the two softmax warps of a sub-partition (one per lane): named barriers of 64 threads, one
+// warp syncs (waits for its turn), the other arrives (passes the turn on).
+__device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 // One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that hold at
 // least one existing key (4 for a full tile), MASK = the last of them is partial.  g = index of the tile in the CTA's
@@ -121,6 +133,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
     const float neg_m = -m_used;
     const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_m, neg_m);
     uint64_t sum2[2] = {0ull, 0ull};
+    turn_wait(b.turn_mine);            // the SFU is this lane's from here ...
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -139,6 +152,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
             v[c][i / 2] = pack_bf16x2(e0, e1);
             v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
         }
+    turn_pass(b.turn_other);           // ... to here
     {
         float s0, s1, s2, s3;
         f2_unpack(sum2[0], s0, s1);
@@ -176,22 +190,28 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
 }
 
 template <int P4>
-__global__ void __launch_bounds__(kThreads, 2)
-attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) {
+__global__ void __launch_bounds__(kThreads, 1)
+attn_pp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnPpArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[kNumBars];
+    __shared__ __align__(8) uint64_t bars_all[kLanes * kNumBars];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();
+    // which work stream ("lane") this warp serves, and the stream's place among the 2 * gridDim.x streams of the grid
+    const int ln = warp < 4 * kLanes ? (warp >> 2) : ((warp - 4 * kLanes) & 1);
+    const int vb = kLanes * static_cast<int>(blockIdx.x) + ln, vgrid = kLanes * static_cast<int>(gridDim.x);
     const int nkv = (p.T + kKV - 1) / kKV;
-    const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int total = my_items * nkv;          // key tiles this CTA walks through, in order
+    auto items_of = [&](int v) { return v < p.n_items ? (p.n_items - v + vgrid - 1) / vgrid : 0; };
+    const int total = items_of(vb) * nkv;          // key tiles this lane walks through, in order
+    const int total_other = items_of(vb ^ 1) * nkv;
     const int n_pv = 16 * p.k16;
+    uint64_t* bars = bars_all + ln * kNumBars;
 
-    const uint32_t base = smem_u32(smem_raw);
-    if ((base & 1023u) != 0u) __trap();
+    const uint32_t base0 = smem_u32(smem_raw);
+    if ((base0 & 1023u) != 0u) __trap();
+    const uint32_t base = base0 + static_cast<uint32_t>(ln) * kLaneSmem;
     const uint32_t sQ = base;                              // Q buffer b at + b * kQBytes
     const uint32_t sK = sQ + kQSlots * kQBytes;            // K slot s at + s * tile
     const uint32_t sV = sK + kKSlots * kTileBytes;         // V slot s at + s * tile
@@ -206,7 +226,7 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
     const uint32_t bar_p_full = bar_s_full + 16;                 // P(g) (and rescaled O) in TMEM  (4 warps)
     const uint32_t bar_pv_done = bar_s_full + 24;                // PV(g) complete                 (MMA commit)
 
-    if (threadIdx.x == 0) {
+    if (warp == kProducerWarp0 + ln && lane == 0) {       // one thread per lane initialises that lane's barriers
         for (int s = 0; s < 2 * kRing; ++s) mbar_init(bar_kfull + 8 * s, 1);
         mbar_init(bar_s_full, 1);
         mbar_init(bar_s_free, 4);
@@ -214,24 +234,24 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
         mbar_init(bar_pv_done, 1);
         fence_mbar_init();
     }
-    if (warp == kMmaWarp) {
-        tmem_alloc(smem_u32(&tmem_base_s), kTmemCols);
+    if (warp == kMmaWarp0) {
+        tmem_alloc(smem_u32(&tmem_base_s), kLanes * kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = tmem_base_s + static_cast<uint32_t>(ln) * kTmemCols;
     pdl_wait();       // set-up above overlapped the previous kernel; q/k/v are read from here on
 
-    if (warp == kProducerWarp) {
+    if (warp >= kProducerWarp0 && warp < kMmaWarp0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&tmQKV);
             int ks = 0, vs = 0;
             uint32_t kphase = 0, vphase = 0;
             int it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            for (int item = vb; item < p.n_items; item += vgrid, ++it) {
                 const int bh = item / p.nq, q0 = (item - bh * p.nq) * kQ;
                 const int b = bh / p.H, h = bh - b * p.H;
                 const int row_base = b * p.T;
@@ -255,7 +275,7 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp >= kMmaWarp0) {
         // ------------------------------ MMA issuer --------------------------------
         // The whole warp runs the loop (warp-uniform control flow); only the tcgen05 instructions are issued by one
         // elected lane.  Step g issues QK^T(g) and then PV(g-1): the first QK^T of the next work item goes out before
@@ -332,10 +352,12 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
         const int quad = warp & 3;                          // TMEM lane quadrant of this warp
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + kColS, tP = tmem_base + lane_off + kColP, tO = tmem_base + lane_off + kColO;
-        const TileBars tb{bar_s_free, bar_pv_done, bar_p_full};
+        // turn barriers of this sub-partition's pair of softmax warps: id 1 + 4 * lane-of-the-owner + quad
+        const TileBars tb{bar_s_free, bar_pv_done, bar_p_full, 1 + 4 * ln + quad, 1 + 4 * (ln ^ 1) + quad};
+        if (ln == 1) turn_pass(tb.turn_other);          // lane 0 exponentiates first
         float m_used = -INFINITY;      // running maximum in the scaled log2 domain
         float l = 0.f;                 // running sum of p
-        int j = 0, item = blockIdx.x;
+        int j = 0, item = vb;
         for (int g = 0; g < total; ++g) {
             const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
             const bool first = j == 0;
@@ -384,25 +406,27 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
                     }
                 }
                 tc_fence_before();         // the O reads above are ordered before this warp's next p_full arrive
-                j = 0; item += gridDim.x;
+                j = 0; item += vgrid;
                 m_used = -INFINITY; l = 0.f;
             }
         }
+        // the partner lane may have more tiles left (work items differ by at most one): keep taking and passing turns
+        for (int g = total; g < total_other; ++g) { turn_wait(tb.turn_mine); turn_pass(tb.turn_other); }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == kMmaWarp0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base_s, kLanes * kTmemCols);
     }
 }
 
 }  // namespace
 
-cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
+cudaError_t attn_pp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
     const AttnDesc& d = plan.desc;
-    AttnTcpArgs a;
+    AttnPpArgs a;
     a.ctx = static_cast<__nv_bfloat16*>(d.ctx);
     a.ldo = d.ldo;
     a.T = d.T;
@@ -412,16 +436,17 @@ cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stre
     a.nq = (d.T + kQ - 1) / kQ;
     a.n_items = d.B * d.H * a.nq;
     a.scale_log2 = d.scale * 1.4426950408889634f;
-    const size_t smem = static_cast<size_t>(kQSlots) * kQBytes + static_cast<size_t>(kKSlots + kVSlots) * kTileBytes;
-    const int grid = a.n_items < 2 * num_sms ? a.n_items : 2 * num_sms;
+    const size_t smem = static_cast<size_t>(kLanes) * kLaneSmem;
+    const int pairs = (a.n_items + kLanes - 1) / kLanes;
+    const int grid = pairs < num_sms ? pairs : num_sms;
     // share of the exponentials computed on the FMA pipe, in pairs per four pairs (VITDET_ATTN_POLY=0..4 overrides; A/B switch)
     static int p4 = -1;
     if (p4 < 0) { const char* e = getenv("VITDET_ATTN_POLY"); p4 = e ? atoi(e) : kDefaultPoly; if (p4 < 0 || p4 > 4) p4 = kDefaultPoly; }
 #define VITDET_LAUNCH(P)                                                                                                  \
     {                                                                                                                     \
-        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tcp_kernel<P>), static_cast<int>(smem)); \
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_pp_kernel<P>), static_cast<int>(smem)); \
         if (e != cudaSuccess) return e;                                                                                   \
-        return launch_kernel(attn_tcp_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
+        return launch_kernel(attn_pp_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
     }
     switch (p4) {
         case 1: VITDET_LAUNCH(1)

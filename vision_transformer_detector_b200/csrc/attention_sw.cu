@@ -1,18 +1,20 @@
-// Multi-head self-attention core, PERSISTENT form: softmax(q k^T / sqrt(d)) v per (image, head) on tcgen05 without
-// materialising the (B, H, T, T) score tensor of keras.layers.MultiHeadAttention (reference det.py:364-369).
+// Multi-head self-attention core: persistent kernel with a SOFTWARE-PIPELINED softmax warp — softmax(q k^T / sqrt(d)) v
+// per (image, head) on tcgen05 without materialising the (B, H, T, T) score tensor of keras.layers.MultiHeadAttention
+// (reference det.py:364-369).
 //
-// Same per-tile machinery as attention_tc.cu (one softmax thread per query row, S | P | O in 256 TMEM columns, P fed to
-// the PV product from tensor memory, lazy rescale, two CTAs per SM), but a CTA no longer lives for one 128-query work
-// item: the per-instruction samples of that kernel (profiles/r02_attention_analysis.md) put a fifth of the softmax warps'
-// time into the start and the end of a CTA — TMEM allocation + barrier set-up, the first Q / K tiles' flight from L2,
-// the first QK^T, and the final drain — during which the SFU, the binding unit, idles.  Here the grid is 2 x #SM CTAs
-// and every role loops over a FLAT sequence of key tiles g = 0 .. items * tiles-per-item - 1:
-//   warp 4  TMA producer: Q of item i+1 into the second Q buffer while item i computes; K tiles through a 2-slot ring and
-//           V tiles through a 3-slot ring (K(j) is free once QK^T(j) has run, V(j) only after PV(j) a tile later)
-//   warp 5  MMA issuer: QK^T(g + 1) is issued as soon as the softmax warps hold S(g) in registers — also across an item
-//           boundary, so the first scores of the next item are ready before the current item's last P is written
-//   warps 0..3  softmax; the last tile of an item is followed by O / l -> ctx and a reset of the running statistics
-// TMEM allocation, barrier initialisation and tensor-map prefetch happen once per CTA.
+// What bounds the earlier kernels (profiles/r02_attention_analysis.md): the SFU accepts one warp-wide ex2 every 8 clocks
+// per SM sub-partition, but ONE warp gets at most one in every ~16 — so the SFU is only saturated while both softmax
+// warps of a sub-partition (two CTAs per SM) are inside their exponential phase, and every clock a warp spends on
+// anything else (TMEM load of the next scores, row maximum, P to TMEM, barrier hand-offs: ~900 of ~3000 clocks per
+// tile) is SFU time lost.  More warps (split rows), explicit turn-taking and FMA-pipe exponentials were all measured and
+// lost; what is left is to take the "anything else" off the warp's critical path.  A warp issues a MUFU every 16 clocks
+// and has ~13 free issue slots in between: here the per-tile work is reordered so that those slots carry the next
+// tile's work.  Per 32-key chunk c of tile g the warp
+//     exponentiates chunk c of S(g) (registers) and stores that quarter of P(g) to TMEM,
+//     reloads the freed registers with chunk c of S(g+1) (QK^T(g+1) ran while S(g) was being exponentiated),
+//     folds chunk c-1 of S(g+1) — loaded one chunk earlier — into the next row maximum,
+// so TMEM latency, the maximum and the stores overlap the exponentials of the same warp.  Everything around the softmax
+// warps (persistent flat tile loop, Q double-buffered, split K / V rings, MMA issue order) is attention_tcp.cu's.
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -39,7 +41,7 @@ constexpr int kRing = kKSlots + kVSlots + kQSlots;
 constexpr int kNumBars = 2 * kRing + 4;
 constexpr int kDefaultPoly = 0;
 
-struct AttnTcpArgs {
+struct AttnSwArgs {
     __nv_bfloat16* ctx;
     int ldo;
     int T, H;
@@ -80,104 +82,45 @@ __device__ __forceinline__ void exp2_pair_poly(uint64_t t2, float& e0, float& e1
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
-struct TileBars { uint32_t s_free, pv_done, p_full; };
 
-// One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that hold at
-// least one existing key (4 for a full tile), MASK = the last of them is partial.  g = index of the tile in the CTA's
-// flat sequence (barrier parities), first = first tile of a work item (nothing to rescale, O is overwritten).
-// P4 of every four score pairs take the polynomial path instead of the SFU.
-template <int NCH, bool MASK, int P4>
-__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t tO, const TileBars& b, int lane, int g, bool first,
-                                             int valid, float scale_log2, float& m_used, float& l) {
-    uint32_t v[NCH][32];
+// exponentials of one 32-key chunk held in v[0..32): p = 2^(s*c - m) in place as packed bf16 pairs in pk[0..16), row sum
+// accumulated in sum2.  P4 of every four score pairs take the polynomial path instead of the SFU.
+template <int P4>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t sc2, uint64_t nm2, uint64_t (&sum2)[2]) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tS + 32u * c, v[c]);
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(b.s_free);          // S(g) is in registers: QK^T(g+1) may overwrite it
+    for (int i = 0; i < 32; i += 4) {
+        float t0, t1, t2, t3;
+        const uint64_t ta = f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+        const uint64_t tb = f2_fma(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, nm2);
+        float e0, e1, e2, e3;
+        if (((i >> 1) & 3) < P4) exp2_pair_poly(ta, e0, e1);
+        else { f2_unpack(ta, t0, t1); e0 = ex2f(t0); e1 = ex2f(t1); }      // ex2(-inf) = 0
+        if ((((i >> 1) + 1) & 3) < P4) exp2_pair_poly(tb, e2, e3);
+        else { f2_unpack(tb, t2, t3); e2 = ex2f(t2); e3 = ex2f(t3); }
+        sum2[0] = f2_add(sum2[0], f2_pack(e0, e1));
+        sum2[1] = f2_add(sum2[1], f2_pack(e2, e3));
+        pk[i / 2] = pack_bf16x2(e0, e1);
+        pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+    }
+}
 
-    if (MASK) {
+// masks the keys past the end of the image (chunk `c` of a tile with `valid` existing keys) and folds the chunk into mx
+__device__ __forceinline__ void max_chunk(uint32_t (&v)[32], int c, int valid, float (&mx)[4]) {
+    if (32 * c + 32 > valid) {          // warp-uniform: only the last chunk of an image's last tile
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (32 * (NCH - 1) + i >= valid) v[NCH - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
-    }
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
-            mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
-        }
-    const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2);
-    const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile of an item
-    float alpha = 1.f;
-    if (grow) {
-        alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
-        m_used = m_new;
-        l *= alpha;
-    }
-    const float neg_m = -m_used;
-    const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_m, neg_m);
-    uint64_t sum2[2] = {0ull, 0ull};
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float t0, t1, t2, t3;
-            const uint64_t ta = f2_fma(f2_pack(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2);
-            const uint64_t tb = f2_fma(f2_pack(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])), sc2, nm2);
-            float e0, e1, e2, e3;
-            // pairs (i/2) % 4 = 0..3 of a group of eight scores; the first P4 of them go to the FMA pipe
-            if (((i >> 1) & 3) < P4) exp2_pair_poly(ta, e0, e1);
-            else { f2_unpack(ta, t0, t1); e0 = ex2f(t0); e1 = ex2f(t1); }      // ex2(-inf) = 0
-            if ((((i >> 1) + 1) & 3) < P4) exp2_pair_poly(tb, e2, e3);
-            else { f2_unpack(tb, t2, t3); e2 = ex2f(t2); e3 = ex2f(t3); }
-            sum2[0] = f2_add(sum2[0], f2_pack(e0, e1));
-            sum2[1] = f2_add(sum2[1], f2_pack(e2, e3));
-            v[c][i / 2] = pack_bf16x2(e0, e1);
-            v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
-        }
-    {
-        float s0, s1, s2, s3;
-        f2_unpack(sum2[0], s0, s1);
-        f2_unpack(sum2[1], s2, s3);
-        l += (s0 + s1) + (s2 + s3);
-    }
-
-    // P (and O) must no longer be in use by PV(g-1)
-    if (g > 0) {
-        mbar_wait(b.pv_done, (g - 1) & 1);
-        tc_fence_after();
-        if (grow && !first) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld_32x32(tO + 32u * c, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st_32x32_x32(tO + 32u * c, o);
-            }
-        }
+            if (32 * c + i >= valid) v[i] = 0xff800000u;     // -inf
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = (c < NCH) ? v[c < NCH ? c : 0][i] : 0u;     // P = 0 for keys that do not exist
-        tmem_st_32x32_x16(tP + 16u * c, pk);
+    for (int i = 0; i < 32; i += 4) {
+        mx[0] = fmaxf(mx[0], __uint_as_float(v[i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[i + 1]));
+        mx[2] = fmaxf(mx[2], __uint_as_float(v[i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[i + 3]));
     }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(b.p_full);
 }
 
 template <int P4>
 __global__ void __launch_bounds__(kThreads, 2)
-attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) {
+attn_sw_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnSwArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[kNumBars];
     __shared__ uint32_t tmem_base_s;
@@ -332,29 +275,105 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
         const int quad = warp & 3;                          // TMEM lane quadrant of this warp
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + kColS, tP = tmem_base + lane_off + kColP, tO = tmem_base + lane_off + kColO;
-        const TileBars tb{bar_s_free, bar_pv_done, bar_p_full};
         float m_used = -INFINITY;      // running maximum in the scaled log2 domain
         float l = 0.f;                 // running sum of p
         int j = 0, item = blockIdx.x;
-        for (int g = 0; g < total; ++g) {
-            const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
-            const bool first = j == 0;
-            mbar_wait(bar_s_full, g & 1);
-            tc_fence_after();
-#define VITDET_TILE(NCH, MASK) softmax_tile<NCH, MASK, P4>(tS, tP, tO, tb, lane, g, first, valid, p.scale_log2, m_used, l)
-            if (valid == kKV) {
-                VITDET_TILE(4, false);
-            } else {
-                // last tile of the image: only the chunks with existing keys are loaded and exponentiated; warp-uniform
-                const bool partial = (valid & 31) != 0;
-                switch ((valid + 31) >> 5) {
-                    case 1: if (partial) VITDET_TILE(1, true); else VITDET_TILE(1, false); break;
-                    case 2: if (partial) VITDET_TILE(2, true); else VITDET_TILE(2, false); break;
-                    case 3: if (partial) VITDET_TILE(3, true); else VITDET_TILE(3, false); break;
-                    default: VITDET_TILE(4, true); break;
-                }
+        uint32_t v[4][32];             // the scores of the tile being exponentiated; refilled chunk by chunk with the next tile's
+        float alpha = 1.f;
+        bool grow = false;
+        auto valid_of = [&](int jj) { return min(kKV, p.T - jj * kKV); };
+        // row statistics of the tile whose scores are in v (called once all its chunks went through max_chunk)
+        auto stats = [&](const float (&mx)[4]) {
+            const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2);
+            grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile of an item
+            alpha = 1.f;
+            if (grow) {
+                alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
+                m_used = m_new;
+                l *= alpha;
             }
-#undef VITDET_TILE
+        };
+        if (total > 0) {
+            // ---- prologue: S(0) into registers, its row maximum ----
+            const int valid = valid_of(0), nch = (valid + 31) >> 5;
+            mbar_wait(bar_s_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) tmem_ld_32x32(tS + 32u * c, v[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_s_free);
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) max_chunk(v[c], c, valid, mx);
+            stats(mx);
+        }
+        for (int g = 0; g < total; ++g) {
+            // here: v = S(g), (m_used, l, alpha, grow) already account for tile g's maximum
+            const bool first = j == 0;
+            const int nch = (valid_of(j) + 31) >> 5;                       // chunks of this tile that hold existing keys
+            const bool have_next = g + 1 < total;
+            const int jn = (j + 1 == nkv) ? 0 : j + 1;
+            const int valid_n = valid_of(jn), nch_n = have_next ? (valid_n + 31) >> 5 : 0;
+            const float neg_m = -m_used;
+            const uint64_t sc2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(neg_m, neg_m);
+            uint64_t sum2[2] = {0ull, 0ull};
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+                if (c < nch) {
+                    exp_chunk<P4>(v[c], pk, sc2, nm2, sum2);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u;               // P = 0 for keys that do not exist
+                }
+                if (c == 0) {
+                    // P and O must no longer be in use by PV(g-1): it was issued when this warp finished tile g-1 and has
+                    // had the first chunk's exponentials to complete
+                    if (g > 0) {
+                        mbar_wait(bar_pv_done, (g - 1) & 1);
+                        tc_fence_after();
+                        if (grow && !first) {
+#pragma unroll
+                            for (int h2 = 0; h2 < 4; ++h2) {
+                                if (16 * h2 >= n_pv) break;
+                                uint32_t o[16];
+                                tmem_ld_32x32_x16(tO + 16u * h2, o);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                                tmem_st_32x32_x16(tO + 16u * h2, o);
+                            }
+                        }
+                    }
+                    if (have_next) { mbar_wait(bar_s_full, (g + 1) & 1); tc_fence_after(); }     // QK^T(g+1) ran during tile g-1's tail
+                }
+                tmem_st_32x32_x16(tP + 16u * c, pk);
+                if (c > 0 && c - 1 < nch_n) {
+                    tmem_ld_wait();                                        // chunk c-1 of S(g+1), loaded one chunk ago
+                    max_chunk(v[c - 1], c - 1, valid_n, mx);
+                }
+                if (c < nch_n) tmem_ld_32x32(tS + 32u * c, v[c]);          // the registers of chunk c are free again
+            }
+            {
+                float s0, s1, s2, s3;
+                f2_unpack(sum2[0], s0, s1);
+                f2_unpack(sum2[1], s2, s3);
+                l += (s0 + s1) + (s2 + s3);
+            }
+            tmem_st_wait();
+            if (nch_n > 0) tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_p_full);                                   // P(g) (and the rescaled O) are in TMEM
+                if (have_next) mbar_arrive(bar_s_free);                    // S(g+1) is in registers: QK^T(g+2) may overwrite it
+            }
+            if (3 < nch_n) max_chunk(v[3], 3, valid_n, mx);
             if (++j == nkv) {
                 // ---- end of the work item: O / l -> bf16 context rows, statistics reset ----
                 mbar_wait(bar_pv_done, g & 1);
@@ -365,21 +384,21 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
                 const float inv = 1.f / l;
                 __nv_bfloat16* orow = p.ctx + static_cast<size_t>(b * p.T + (q < p.T ? q : 0)) * p.ldo + h * p.hp;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (32 * c >= p.hp) break;
-                    uint32_t o[32];
-                    tmem_ld_32x32(tO + 32u * c, o);
+                for (int h2 = 0; h2 < 4; ++h2) {
+                    if (16 * h2 >= p.hp) break;
+                    uint32_t o[16];
+                    tmem_ld_32x32_x16(tO + 16u * h2, o);
                     tmem_ld_wait();
                     if (q < p.T) {
 #pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            if (32 * c + 8 * gq >= p.hp) break;          // the head holds hp columns
+                        for (int gq = 0; gq < 2; ++gq) {
+                            if (16 * h2 + 8 * gq >= p.hp) break;          // the head holds hp columns
                             uint4 w;
                             w.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
                             w.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
                             w.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
                             w.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
-                            *reinterpret_cast<uint4*>(orow + 32 * c + 8 * gq) = w;
+                            *reinterpret_cast<uint4*>(orow + 16 * h2 + 8 * gq) = w;
                         }
                     }
                 }
@@ -387,6 +406,7 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
                 j = 0; item += gridDim.x;
                 m_used = -INFINITY; l = 0.f;
             }
+            if (have_next) stats(mx);      // tile g+1's maximum against the (possibly reset) running statistics
         }
     }
 
@@ -400,9 +420,9 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
 
 }  // namespace
 
-cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
+cudaError_t attn_sw_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
     const AttnDesc& d = plan.desc;
-    AttnTcpArgs a;
+    AttnSwArgs a;
     a.ctx = static_cast<__nv_bfloat16*>(d.ctx);
     a.ldo = d.ldo;
     a.T = d.T;
@@ -419,9 +439,9 @@ cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stre
     if (p4 < 0) { const char* e = getenv("VITDET_ATTN_POLY"); p4 = e ? atoi(e) : kDefaultPoly; if (p4 < 0 || p4 > 4) p4 = kDefaultPoly; }
 #define VITDET_LAUNCH(P)                                                                                                  \
     {                                                                                                                     \
-        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tcp_kernel<P>), static_cast<int>(smem)); \
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_sw_kernel<P>), static_cast<int>(smem)); \
         if (e != cudaSuccess) return e;                                                                                   \
-        return launch_kernel(attn_tcp_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
+        return launch_kernel(attn_sw_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
     }
     switch (p4) {
         case 1: VITDET_LAUNCH(1)

@@ -1,18 +1,19 @@
-// Multi-head self-attention core, PERSISTENT form: softmax(q k^T / sqrt(d)) v per (image, head) on tcgen05 without
-// materialising the (B, H, T, T) score tensor of keras.layers.MultiHeadAttention (reference det.py:364-369).
+// Multi-head self-attention core: PERSISTENT kernel with the score row of a query SPLIT OVER TWO WARPS
+// (keras.layers.MultiHeadAttention, reference det.py:364-369).
 //
-// Same per-tile machinery as attention_tc.cu (one softmax thread per query row, S | P | O in 256 TMEM columns, P fed to
-// the PV product from tensor memory, lazy rescale, two CTAs per SM), but a CTA no longer lives for one 128-query work
-// item: the per-instruction samples of that kernel (profiles/r02_attention_analysis.md) put a fifth of the softmax warps'
-// time into the start and the end of a CTA — TMEM allocation + barrier set-up, the first Q / K tiles' flight from L2,
-// the first QK^T, and the final drain — during which the SFU, the binding unit, idles.  Here the grid is 2 x #SM CTAs
-// and every role loops over a FLAT sequence of key tiles g = 0 .. items * tiles-per-item - 1:
-//   warp 4  TMA producer: Q of item i+1 into the second Q buffer while item i computes; K tiles through a 2-slot ring and
-//           V tiles through a 3-slot ring (K(j) is free once QK^T(j) has run, V(j) only after PV(j) a tile later)
-//   warp 5  MMA issuer: QK^T(g + 1) is issued as soon as the softmax warps hold S(g) in registers — also across an item
-//           boundary, so the first scores of the next item are ready before the current item's last P is written
-//   warps 0..3  softmax; the last tile of an item is followed by O / l -> ctx and a reset of the running statistics
-// TMEM allocation, barrier initialisation and tensor-map prefetch happen once per CTA.
+// The two measured limits of the earlier kernels (profiles/r02_attention_analysis.md):
+//   * a softmax warp issues at most one MUFU.EX2 every ~16 cycles, while the SFU of its SM sub-partition accepts one
+//     every 8: with one softmax thread per query row (attention_tc.cu / attention_tcp.cu: two softmax warps per
+//     sub-partition, each in its exponential phase 70 % of the time) the SFU cannot be more than ~2/3 busy;
+//   * with the row split over warp pairs but one CTA per work item (attention_tc8.cu) the SFU queue does saturate inside
+//     the exponential phases, but a work item is then so short (64 exponentials per thread and tile) that CTA start-up,
+//     the first Q/K flight and the final drain dominate.
+// This kernel combines the two remedies: eight softmax warps per CTA (warps w and w + 4 share TMEM lane quadrant w & 3,
+// warp `half` owns keys [64 half, +64) of every tile; four exponentiating warps per sub-partition at two CTAs per SM) AND
+// the flat, persistent tile loop of attention_tcp.cu (Q double-buffered, K / V in separate 2- / 3-slot rings, QK^T of the
+// next work item issued before the last PV of the current one).  The pair shares the row maximum through shared memory
+// (one float per row and tile + a 64-thread named barrier) and combines the row sums at the end of a work item.
+//   warps 0..7  softmax (quad = w & 3, half = w >> 2)     warp 8  TMA producer     warp 9  TMEM allocation + MMA issue
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -26,9 +27,10 @@ namespace {
 constexpr int kQ = 128;            // queries per work item (UMMA M)
 constexpr int kKV = 128;           // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kHP = 64;            // head pitch in shared memory (one 128-byte swizzle row of bf16)
-constexpr int kKSlots = 2, kVSlots = 3, kQSlots = 2;
-constexpr int kThreads = 192;
-constexpr int kProducerWarp = 4, kMmaWarp = 5;      // highest warp ids: favoured by the arbiter
+constexpr int kKSlots = 2, kVSlots = 2, kQSlots = 2;      // 96 KB: with the 2 KB exchange buffer two CTAs fit an SM (V(g+1) loads while tile g is exponentiated)
+constexpr int kSoftmaxWarps = 8;
+constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
+constexpr int kProducerWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;      // highest warp ids: favoured by the arbiter
 constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
 constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one K tile or one V tile = two TMA boxes of 64 rows
 constexpr int kBoxBytes = 64 * kHP * 2;
@@ -39,7 +41,7 @@ constexpr int kRing = kKSlots + kVSlots + kQSlots;
 constexpr int kNumBars = 2 * kRing + 4;
 constexpr int kDefaultPoly = 0;
 
-struct AttnTcpArgs {
+struct AttnTc8pArgs {
     __nv_bfloat16* ctx;
     int ldo;
     int T, H;
@@ -82,36 +84,45 @@ __device__ __forceinline__ void exp2_pair_poly(uint64_t t2, float& e0, float& e1
 
 struct TileBars { uint32_t s_free, pv_done, p_full; };
 
-// One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that hold at
-// least one existing key (4 for a full tile), MASK = the last of them is partial.  g = index of the tile in the CTA's
-// flat sequence (barrier parities), first = first tile of a work item (nothing to rescale, O is overwritten).
-// P4 of every four score pairs take the polynomial path instead of the SFU.
-template <int NCH, bool MASK, int P4>
-__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t tO, const TileBars& b, int lane, int g, bool first,
-                                             int valid, float scale_log2, float& m_used, float& l) {
-    uint32_t v[NCH][32];
+__device__ __forceinline__ void pair_barrier(int quad) {       // the two warps of a TMEM lane quadrant
+    asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+}
+
+// One key tile of the online softmax for the calling thread's (query row, key half): NC = number of 32-key chunks of the
+// half that hold at least one existing key (2 for a full tile, 0 when the half lies past the end of the image), MASK =
+// the last of them is partial.  g = index of the tile in the CTA's flat sequence (barrier parities), first = first tile of
+// a work item.  P4 of every four score pairs take the polynomial path instead of the SFU.
+template <int NC, bool MASK, int P4>
+__device__ __forceinline__ void softmax_half_tile(uint32_t tS, uint32_t tP, uint32_t tO, const TileBars& b, float* xch_mine,
+                                                  const float* xch_other, int lane, int quad, int half, int g, bool first,
+                                                  int valid_h, int n_pv, float scale_log2, float& m_used, float& l) {
+    uint32_t v[NC > 0 ? NC : 1][32];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tS + 32u * c, v[c]);
-    tmem_ld_wait();
+    for (int c = 0; c < NC; ++c) tmem_ld_32x32(tS + 32u * c, v[c]);
+    if (NC > 0) tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(b.s_free);          // S(g) is in registers: QK^T(g+1) may overwrite it
+    if (lane == 0) mbar_arrive(b.s_free);           // S(g) is in registers (or not needed): QK^T(g+1) may overwrite it
 
     if (MASK) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (32 * (NCH - 1) + i >= valid) v[NCH - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
+            if (32 * (NC - 1) + i >= valid_h) v[NC - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
     }
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
             mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
         }
-    const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2);
-    const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile of an item
+    // both halves of the row must scale P(g) against the same reference: exchange the half-row maxima
+    *xch_mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    pair_barrier(quad);
+    const float m_row = fmaxf(*xch_mine, *xch_other);
+    const float m_new = fmaxf(m_used, m_row * scale_log2);
+    const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile; same in both warps
     float alpha = 1.f;
     if (grow) {
         alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
@@ -122,14 +133,13 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
     const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_m, neg_m);
     uint64_t sum2[2] = {0ull, 0ull};
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             float t0, t1, t2, t3;
             const uint64_t ta = f2_fma(f2_pack(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2);
             const uint64_t tb = f2_fma(f2_pack(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])), sc2, nm2);
             float e0, e1, e2, e3;
-            // pairs (i/2) % 4 = 0..3 of a group of eight scores; the first P4 of them go to the FMA pipe
             if (((i >> 1) & 3) < P4) exp2_pair_poly(ta, e0, e1);
             else { f2_unpack(ta, t0, t1); e0 = ex2f(t0); e1 = ex2f(t1); }      // ex2(-inf) = 0
             if ((((i >> 1) + 1) & 3) < P4) exp2_pair_poly(tb, e2, e3);
@@ -150,23 +160,20 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
     if (g > 0) {
         mbar_wait(b.pv_done, (g - 1) & 1);
         tc_fence_after();
-        if (grow && !first) {
+        if (grow && !first && 32 * half < n_pv) {         // this warp rescales O columns [32 half, +32)
+            uint32_t o[32];
+            tmem_ld_32x32(tO + 32u * half, o);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld_32x32(tO + 32u * c, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st_32x32_x32(tO + 32u * c, o);
-            }
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32_x32(tO + 32u * half, o);
         }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = (c < NCH) ? v[c < NCH ? c : 0][i] : 0u;     // P = 0 for keys that do not exist
+        for (int i = 0; i < 16; ++i) pk[i] = (c < NC) ? v[c < NC ? c : 0][i] : 0u;     // P = 0 for keys that do not exist
         tmem_st_32x32_x16(tP + 16u * c, pk);
     }
     tmem_st_wait();
@@ -177,10 +184,11 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
 
 template <int P4>
 __global__ void __launch_bounds__(kThreads, 2)
-attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) {
+attn_tc8p_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTc8pArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[kNumBars];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float xch[2][2][kQ];        // [tile parity][key half][query row]: half-row maxima, and the row sums at the end
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -209,8 +217,8 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2 * kRing; ++s) mbar_init(bar_kfull + 8 * s, 1);
         mbar_init(bar_s_full, 1);
-        mbar_init(bar_s_free, 4);
-        mbar_init(bar_p_full, 4);
+        mbar_init(bar_s_free, kSoftmaxWarps);
+        mbar_init(bar_p_full, kSoftmaxWarps);
         mbar_init(bar_pv_done, 1);
         fence_mbar_init();
     }
@@ -329,61 +337,83 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
         }
     } else {
         // ------------------------------ softmax -----------------------------------
-        const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+        const int quad = warp & 3, half = warp >> 2;        // TMEM lane quadrant; which 64 keys of every tile
+        const int r = quad * 32 + lane;                     // query row within the tile
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tS = tmem_base + lane_off + kColS, tP = tmem_base + lane_off + kColP, tO = tmem_base + lane_off + kColO;
+        const uint32_t tS = tmem_base + lane_off + kColS + 64u * half;
+        const uint32_t tP = tmem_base + lane_off + kColP + 32u * half;
+        const uint32_t tO = tmem_base + lane_off + kColO;
         const TileBars tb{bar_s_free, bar_pv_done, bar_p_full};
-        float m_used = -INFINITY;      // running maximum in the scaled log2 domain
-        float l = 0.f;                 // running sum of p
+        float m_used = -INFINITY;      // running maximum in the scaled log2 domain (identical in both warps of a pair)
+        float l = 0.f;                 // running sum of p over this warp's key half
         int j = 0, item = blockIdx.x;
+        int xp = 0;                    // parity of the exchange buffer (advances with every pair barrier)
         for (int g = 0; g < total; ++g) {
             const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
+            const int valid_h = max(0, min(64, valid - 64 * half));
             const bool first = j == 0;
+            const int q0 = (item % p.nq) * kQ;
+            const bool rows_exist = q0 + quad * 32 < p.T;   // warp-uniform, and the same in both warps of the pair
             mbar_wait(bar_s_full, g & 1);
             tc_fence_after();
-#define VITDET_TILE(NCH, MASK) softmax_tile<NCH, MASK, P4>(tS, tP, tO, tb, lane, g, first, valid, p.scale_log2, m_used, l)
-            if (valid == kKV) {
-                VITDET_TILE(4, false);
+            if (!rows_exist) {
+                // no query of this warp exists: keep the protocol going, touch nothing
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_s_free);
+                if (g > 0) mbar_wait(bar_pv_done, (g - 1) & 1);      // phase g-1 of p_full is complete before the next arrive
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p_full);
             } else {
-                // last tile of the image: only the chunks with existing keys are loaded and exponentiated; warp-uniform
-                const bool partial = (valid & 31) != 0;
-                switch ((valid + 31) >> 5) {
-                    case 1: if (partial) VITDET_TILE(1, true); else VITDET_TILE(1, false); break;
-                    case 2: if (partial) VITDET_TILE(2, true); else VITDET_TILE(2, false); break;
-                    case 3: if (partial) VITDET_TILE(3, true); else VITDET_TILE(3, false); break;
-                    default: VITDET_TILE(4, true); break;
-                }
-            }
-#undef VITDET_TILE
-            if (++j == nkv) {
-                // ---- end of the work item: O / l -> bf16 context rows, statistics reset ----
-                mbar_wait(bar_pv_done, g & 1);
-                tc_fence_after();
-                const int bh = item / p.nq, q0 = (item - bh * p.nq) * kQ;
-                const int b = bh / p.H, h = bh - b * p.H;
-                const int q = q0 + quad * 32 + lane;
-                const float inv = 1.f / l;
-                __nv_bfloat16* orow = p.ctx + static_cast<size_t>(b * p.T + (q < p.T ? q : 0)) * p.ldo + h * p.hp;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (32 * c >= p.hp) break;
-                    uint32_t o[32];
-                    tmem_ld_32x32(tO + 32u * c, o);
-                    tmem_ld_wait();
-                    if (q < p.T) {
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            if (32 * c + 8 * gq >= p.hp) break;          // the head holds hp columns
-                            uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
-                            w.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
-                            w.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
-                            w.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
-                            *reinterpret_cast<uint4*>(orow + 32 * c + 8 * gq) = w;
-                        }
+                float* xm = &xch[xp][half][r];
+                const float* xo = &xch[xp][half ^ 1][r];
+                xp ^= 1;
+#define VITDET_TILE(NC, MASK) \
+    softmax_half_tile<NC, MASK, P4>(tS, tP, tO, tb, xm, xo, lane, quad, half, g, first, valid_h, n_pv, p.scale_log2, m_used, l)
+                if (valid_h == 64) {
+                    VITDET_TILE(2, false);
+                } else {
+                    // last tile of the image: only the chunks with existing keys are loaded and exponentiated; warp-uniform
+                    const bool partial = (valid_h & 31) != 0;
+                    switch ((valid_h + 31) >> 5) {
+                        case 0: VITDET_TILE(0, false); break;
+                        case 1: if (partial) VITDET_TILE(1, true); else VITDET_TILE(1, false); break;
+                        default: VITDET_TILE(2, true); break;
                     }
                 }
-                tc_fence_before();         // the O reads above are ordered before this warp's next p_full arrive
+#undef VITDET_TILE
+            }
+            if (++j == nkv) {
+                // ---- end of the work item: O / (l_half0 + l_half1) -> bf16 context rows; statistics reset ----
+                if (rows_exist) {
+                    mbar_wait(bar_pv_done, g & 1);
+                    tc_fence_after();
+                    xch[xp][half][r] = l;
+                    pair_barrier(quad);
+                    const float inv = 1.f / (l + xch[xp][half ^ 1][r]);
+                    xp ^= 1;
+                    const int bh = item / p.nq;
+                    const int b = bh / p.H, h = bh - b * p.H;
+                    const int q = q0 + r;
+                    if (32 * half < p.hp) {
+                        uint32_t o[32];
+                        tmem_ld_32x32(tO + 32u * half, o);
+                        tmem_ld_wait();
+                        if (q < p.T) {
+                            __nv_bfloat16* orow = p.ctx + static_cast<size_t>(b * p.T + q) * p.ldo + h * p.hp + 32 * half;
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                if (32 * half + 8 * gq >= p.hp) break;          // the head holds hp columns
+                                uint4 w;
+                                w.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
+                                w.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
+                                w.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
+                                w.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
+                                *reinterpret_cast<uint4*>(orow + 8 * gq) = w;
+                            }
+                        }
+                    }
+                    tc_fence_before();         // the O reads above are ordered before this warp's next p_full arrive
+                }
                 j = 0; item += gridDim.x;
                 m_used = -INFINITY; l = 0.f;
             }
@@ -400,9 +430,9 @@ attn_tcp_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcpArgs p) 
 
 }  // namespace
 
-cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
+cudaError_t attn_tc8p_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream) {
     const AttnDesc& d = plan.desc;
-    AttnTcpArgs a;
+    AttnTc8pArgs a;
     a.ctx = static_cast<__nv_bfloat16*>(d.ctx);
     a.ldo = d.ldo;
     a.T = d.T;
@@ -419,9 +449,9 @@ cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stre
     if (p4 < 0) { const char* e = getenv("VITDET_ATTN_POLY"); p4 = e ? atoi(e) : kDefaultPoly; if (p4 < 0 || p4 > 4) p4 = kDefaultPoly; }
 #define VITDET_LAUNCH(P)                                                                                                  \
     {                                                                                                                     \
-        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tcp_kernel<P>), static_cast<int>(smem)); \
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc8p_kernel<P>), static_cast<int>(smem)); \
         if (e != cudaSuccess) return e;                                                                                   \
-        return launch_kernel(attn_tcp_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
+        return launch_kernel(attn_tc8p_kernel<P>, dim3(grid), dim3(kThreads), smem, stream, 1, plan.tmQKV, a);             \
     }
     switch (p4) {
         case 1: VITDET_LAUNCH(1)

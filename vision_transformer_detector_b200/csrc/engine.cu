@@ -24,8 +24,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vitdet_b200.h"
@@ -69,13 +73,16 @@ static Options env_options() {
     if (const char* e = getenv("VITDET_FUSE_LN")) o.fuse_ln = strcmp(e, "0") != 0;
     if (const char* e = getenv("VITDET_FUSE_TAIL")) o.fuse_tail = strcmp(e, "0") != 0;
     if (const char* e = getenv("VITDET_GEMM_PAIR")) o.gemm_pair = strcmp(e, "0") == 0 ? 0 : (strcmp(e, "all") == 0 ? 2 : 1);
-    if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 40) o.attention = v; }
+    if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 40 || v == 80) o.attention = v; }
     return o;
 }
 
 static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, cudaStream_t st) {
     if (version == 4) return attn_tc_launch(plan, st);
     if (version == 8) return attn_tc8_launch(plan, st);
+    if (version == 80) return attn_tc8p_launch(plan, num_sms, st);
+    if (version == 2) return attn_pp_launch(plan, num_sms, st);
+    if (version == 1) return attn_sw_launch(plan, num_sms, st);
     return attn_tcp_launch(plan, num_sms, st);
 }
 
@@ -208,6 +215,73 @@ struct BlockW {
     std::vector<DenseW> mlp;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Host staging: a caller's ordinary (pageable) array is copied into page-locked memory by a few threads at
+// once — one thread moves ~10 GB/s, far less than the PCIe link the H2D copy then uses — sub-chunk by sub-chunk,
+// so that the asynchronous H2D copy of sub-chunk i runs while sub-chunk i+1 is being staged.
+// ------------------------------------------------------------------------------------------------
+class StagePool {
+public:
+    explicit StagePool(int workers) {
+        for (int i = 0; i < workers; ++i) threads_.emplace_back([this, i] { run(i); });
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // dst[0, bytes) = src[0, bytes), split over the workers and the calling thread; returns when all of it is done
+    void copy(char* dst, const char* src, size_t bytes) {
+        const int parts = static_cast<int>(threads_.size()) + 1;
+        if (parts == 1 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        const size_t per = ((bytes + parts - 1) / parts + 4095) & ~static_cast<size_t>(4095);
+        { std::lock_guard<std::mutex> g(m_); dst_ = dst; src_ = src; bytes_ = bytes; per_ = per; pending_ = parts - 1; ++gen_; }
+        cv_.notify_all();
+        slice(parts - 1);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void slice(int i) {
+        const size_t lo = per_ * static_cast<size_t>(i);
+        if (lo < bytes_) memcpy(dst_ + lo, src_ + lo, (bytes_ - lo) < per_ ? (bytes_ - lo) : per_);
+    }
+    void run(int i) {
+        unsigned long long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(m_); cv_.wait(lk, [&] { return gen_ != seen; }); seen = gen_; if (stop_) return; }
+            slice(i);
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0, per_ = 0;
+    int pending_ = 0;
+};
+
+// One in-flight host submission (vitdet_submit_host .. vitdet_collect): its own pinned staging, device input and
+// record block, so that the H2D copy of submission i+1 overlaps the compute of submission i.
+struct HostSlot {
+    void* pin_in = nullptr; size_t pin_in_bytes = 0;
+    void* pin_out = nullptr; size_t pin_out_bytes = 0;
+    DevBuf dev_in, dev_out;
+    std::vector<cudaEvent_t> copy_events;      // one per staged sub-chunk of images
+    cudaEvent_t done = nullptr;                // recorded after the D2H copy of the record block
+    bool busy = false;
+    size_t R = 0, o_dec = 0, o_id = 0, o_cc = 0, o_cor = 0, o_keep = 0, o_pk = 0;
+    bool has_packed = false;
+    ~HostSlot() {
+        if (pin_in) cudaFreeHost(pin_in);
+        if (pin_out) cudaFreeHost(pin_out);
+        for (auto e : copy_events) cudaEventDestroy(e);
+        if (done) cudaEventDestroy(done);
+    }
+};
+
 }  // namespace vitdet
 
 using namespace vitdet;
@@ -272,18 +346,16 @@ struct vitdet_handle {
     long long launches = 0;             // kernels launched by forward_impl since the last reset
 
     // pinned staging + device buffers for predict_host
-    cudaStream_t copy_stream = nullptr;          // H2D copies of predict_host run here, overlapped with compute
-    std::vector<cudaEvent_t> copy_events;        // one per staged sub-chunk of images
-    void* pin_in = nullptr; size_t pin_in_bytes = 0;
-    void* pin_out = nullptr; size_t pin_out_bytes = 0;
-    DevBuf dev_in, dev_out;
+    cudaStream_t copy_stream = nullptr;          // H2D copies of the host entry points run here, overlapped with compute
+    static constexpr int kHostSlots = 2;
+    HostSlot host_slots[kHostSlots];
+    int next_slot = 0;
+    StagePool* stage_pool = nullptr;             // created on the first pageable submission
 
     ~vitdet_handle() {
         for (auto& r : prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto e : prof_pool) cudaEventDestroy(e);
-        if (pin_in) cudaFreeHost(pin_in);
-        if (pin_out) cudaFreeHost(pin_out);
-        for (auto e : copy_events) cudaEventDestroy(e);
+        delete stage_pool;
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
@@ -858,7 +930,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
     }
     if (det) {
         dout.decoded = det->decoded; dout.class_id = det->class_id; dout.class_conf = det->class_conf;
-        dout.keep = det->keep; dout.corners = det->corners;
+        dout.keep = det->keep; dout.corners = det->corners; dout.packed = det->packed;
     }
     h->head_last = a; h->head_last_ld = lda; h->head_last_f32 = out_f32_act;
     ProfScope ps(h, PC_HEAD_TAIL, st);
@@ -1041,7 +1113,7 @@ int vitdet_set_option(vitdet_handle* h, const char* key, int value) {
     if (k == "fuse_ln") h->opt.fuse_ln = value != 0;
     else if (k == "fuse_tail") h->opt.fuse_tail = value != 0;
     else if (k == "gemm_pair") { if (value < 0 || value > 2) return fail(VITDET_E_INVALID, "set_option(gemm_pair): 0, 1 or 2"); h->opt.gemm_pair = value; }
-    else if (k == "attention") { if (value != 4 && value != 8 && value != 40) return fail(VITDET_E_INVALID, "set_option(attention): 4, 8 or 40"); h->opt.attention = value; }
+    else if (k == "attention") { if (value != 1 && value != 2 && value != 4 && value != 8 && value != 40 && value != 80) return fail(VITDET_E_INVALID, "set_option(attention): 1, 2, 4, 8, 40 or 80"); h->opt.attention = value; }
     else return fail(VITDET_E_NOT_FOUND, "set_option: unknown option '%s'", key);
     h->enc_plans.clear();
     h->head_plans.clear();
@@ -1140,6 +1212,7 @@ int vitdet_decode(const float* logits_dev, int R, const vitdet_decode_params* p,
     dp.corner_scale = p->corner_scale > 0.f ? p->corner_scale : 1.f;
     DecodeOut o;
     o.decoded = out->decoded; o.class_id = out->class_id; o.class_conf = out->class_conf; o.keep = out->keep; o.corners = out->corners;
+    o.packed = out->packed;
     CU_TRY(decode_launch(logits_dev, R, dp, o, static_cast<cudaStream_t>(stream)));
     return 0;
 }
@@ -1191,17 +1264,18 @@ int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_para
     if (R == 0) return 0;
     const size_t r = static_cast<size_t>(R);
     const size_t o_dec = a256(r * 24), o_id = o_dec + a256(r * 24), o_cc = o_id + a256(r * 4), o_cor = o_cc + a256(r * 4),
-                 o_keep = o_cor + a256(r * 16), total = o_keep + a256(r);
+                 o_keep = o_cor + a256(r * 16), o_pk = o_keep + a256(r), total = o_pk + a256(r * 52);
     DevBuf buf;
     RC_TRY(buf.ensure(total));
     char* b = buf.as<char>();
     CU_TRY(cudaMemcpy(b, logits_host, r * 24, cudaMemcpyHostToDevice));
-    vitdet_detections d;
+    vitdet_detections d = {};
     d.decoded = reinterpret_cast<float*>(b + o_dec);
     d.class_id = reinterpret_cast<int32_t*>(b + o_id);
     d.class_conf = reinterpret_cast<float*>(b + o_cc);
     d.corners = reinterpret_cast<int32_t*>(b + o_cor);
     d.keep = reinterpret_cast<uint8_t*>(b + o_keep);
+    if (out_host->packed) d.packed = reinterpret_cast<float*>(b + o_pk);
     RC_TRY(vitdet_decode(reinterpret_cast<const float*>(b), R, p, &d, nullptr));
     CU_TRY(cudaDeviceSynchronize());
     if (out_host->decoded) CU_TRY(cudaMemcpy(out_host->decoded, d.decoded, r * 24, cudaMemcpyDeviceToHost));
@@ -1209,100 +1283,141 @@ int vitdet_decode_host(const float* logits_host, int R, const vitdet_decode_para
     if (out_host->class_conf) CU_TRY(cudaMemcpy(out_host->class_conf, d.class_conf, r * 4, cudaMemcpyDeviceToHost));
     if (out_host->corners) CU_TRY(cudaMemcpy(out_host->corners, d.corners, r * 16, cudaMemcpyDeviceToHost));
     if (out_host->keep) CU_TRY(cudaMemcpy(out_host->keep, d.keep, r, cudaMemcpyDeviceToHost));
+    if (out_host->packed) CU_TRY(cudaMemcpy(out_host->packed, d.packed, r * 52, cudaMemcpyDeviceToHost));
     return 0;
 }
 
 }  // extern "C"
 
-static int predict_host_impl(vitdet_handle* h, const void* images_host, int in_u8, int B, int mode, const vitdet_decode_params* params,
-                             float* logits_host, const vitdet_detections* out_host, void* stream) {
-    if (!h || !images_host || B <= 0 || !params) return fail(VITDET_E_INVALID, "predict_host: bad arguments");
+static int submit_host_impl(vitdet_handle* h, const void* images_host, int in_u8, int B, int mode, const vitdet_decode_params* params,
+                            int want_packed, void* stream, int* ticket) {
+    if (!h || !images_host || B <= 0 || !params || !ticket) return fail(VITDET_E_INVALID, "submit_host: bad arguments");
+    HostSlot& sl = h->host_slots[h->next_slot];
+    if (sl.busy) return fail(VITDET_E_INVALID, "submit_host: %d submissions are in flight; collect one first", vitdet_handle::kHostSlots);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t in_bytes = static_cast<size_t>(B) * h->cfg.image_h * h->cfg.image_w * 3 * (in_u8 ? 1 : 4);
     const size_t R = static_cast<size_t>(B) * h->S;
-    // output record block: logits 24 | decoded 24 | class_id 4 | class_conf 4 | corners 16 | keep 1  bytes per row
-    const size_t o_logits = 0, o_dec = a256(R * 24), o_id = o_dec + a256(R * 24), o_cc = o_id + a256(R * 4),
-                 o_cor = o_cc + a256(R * 4), o_keep = o_cor + a256(R * 16), out_bytes = o_keep + a256(R);
-    if (h->pin_in_bytes < in_bytes) {
-        if (h->pin_in) cudaFreeHost(h->pin_in);
-        h->pin_in = nullptr; h->pin_in_bytes = 0;
-        CU_TRY(cudaHostAlloc(&h->pin_in, in_bytes, cudaHostAllocDefault));
-        h->pin_in_bytes = in_bytes;
+    // output record block: logits 24 | decoded 24 | class_id 4 | class_conf 4 | corners 16 | keep 1 | packed 52  bytes per row
+    sl.R = R; sl.has_packed = want_packed != 0;
+    sl.o_dec = a256(R * 24); sl.o_id = sl.o_dec + a256(R * 24); sl.o_cc = sl.o_id + a256(R * 4); sl.o_cor = sl.o_cc + a256(R * 4);
+    sl.o_keep = sl.o_cor + a256(R * 16); sl.o_pk = sl.o_keep + a256(R);
+    const size_t out_bytes = sl.o_pk + (want_packed ? a256(R * 52) : 0);
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && sl.pin_in_bytes < in_bytes) {
+        if (sl.pin_in) cudaFreeHost(sl.pin_in);
+        sl.pin_in = nullptr; sl.pin_in_bytes = 0;
+        CU_TRY(cudaHostAlloc(&sl.pin_in, in_bytes, cudaHostAllocDefault));
+        sl.pin_in_bytes = in_bytes;
     }
-    if (h->pin_out_bytes < out_bytes) {
-        if (h->pin_out) cudaFreeHost(h->pin_out);
-        h->pin_out = nullptr; h->pin_out_bytes = 0;
-        CU_TRY(cudaHostAlloc(&h->pin_out, out_bytes, cudaHostAllocDefault));
-        h->pin_out_bytes = out_bytes;
+    if (sl.pin_out_bytes < out_bytes) {
+        if (sl.pin_out) cudaFreeHost(sl.pin_out);
+        sl.pin_out = nullptr; sl.pin_out_bytes = 0;
+        CU_TRY(cudaHostAlloc(&sl.pin_out, out_bytes, cudaHostAllocDefault));
+        sl.pin_out_bytes = out_bytes;
     }
-    RC_TRY(h->dev_in.ensure(in_bytes));
-    RC_TRY(h->dev_out.ensure(out_bytes));
-    // Images are copied in sub-chunks of kGran images on a dedicated copy stream, one event per
-    // sub-chunk; the encoder runs chunks of 4, 12 and then `chunk` images, each waiting only for its own
-    // images: at ~12 images/ms of PCIe against ~4 images/ms of compute every copy but the first 4 images'
-    // (0.33 ms) hides behind the previous chunk's compute (measured best of seven schedules, B = 64).  If the caller's
-    // buffer is already page-locked the copy reads it directly; otherwise each sub-chunk is staged
-    // through the handle's pinned buffer first (what a pageable cudaMemcpyAsync would do, serially).
-    // VITDET_E2E_LEAD="g,a,b" overrides the copy granularity and the two lead chunk sizes (tuning experiments)
+    RC_TRY(sl.dev_in.ensure(in_bytes));
+    RC_TRY(sl.dev_out.ensure(out_bytes));
+    if (!sl.done) CU_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    // Images are copied in sub-chunks of kGran images on a dedicated copy stream, one event per sub-chunk; the encoder
+    // runs chunks of 4, 12 and then `chunk` images, each waiting only for its own images: at ~12 images/ms of PCIe
+    // against ~4 images/ms of compute every copy but the first 4 images' (0.33 ms) hides behind the previous chunk's
+    // compute (measured best of seven schedules, B = 64) — and behind the PREVIOUS submission's compute when the caller
+    // keeps two submissions in flight.  A page-locked caller buffer is read directly; a pageable one is staged through
+    // the slot's pinned buffer by the staging threads, sub-chunk by sub-chunk, overlapped with the H2D copies.
+    // VITDET_E2E_LEAD="g,a,b" overrides the copy granularity and the two lead chunk sizes (tuning experiments).
     int kGran = 4, lead0 = 4, lead1 = 12;
     if (in_u8) { kGran = 16; lead0 = 16; lead1 = 0; }       // a quarter of the bytes per image: same 0.3 ms lead-in with 16 images
+    // with the previous submission still computing, this one's copy has a whole forward pass to finish: no small lead chunks
+    if (h->host_slots[(h->next_slot + vitdet_handle::kHostSlots - 1) % vitdet_handle::kHostSlots].busy) { lead0 = 0; lead1 = 0; }
     if (const char* e = getenv("VITDET_E2E_LEAD")) sscanf(e, "%d,%d,%d", &kGran, &lead0, &lead1);
     if (kGran < 1) kGran = 8;
     const int n_sub = (B + kGran - 1) / kGran;
     if (!h->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    while (static_cast<int>(h->copy_events.size()) < n_sub) {
+    while (static_cast<int>(sl.copy_events.size()) < n_sub) {
         cudaEvent_t e;
         CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->copy_events.push_back(e);
+        sl.copy_events.push_back(e);
     }
-    cudaPointerAttributes attr;
-    const bool pinned = cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
+    if (!pinned && !h->stage_pool) {
+        // staging threads (+ the calling thread): a share of the host's cores, divided among the ranks of this node
+        // (LOCAL_WORLD_SIZE under torchrun); VITDET_STAGE_THREADS overrides the total
+        const int hw = static_cast<int>(std::thread::hardware_concurrency());
+        int local_world = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = atoi(e) > 0 ? atoi(e) : 1;
+        int workers = (hw > 0 ? hw / (2 * local_world) : 6) - 1;
+        if (workers > 11) workers = 11;
+        if (workers < 1) workers = 1;
+        if (const char* e = getenv("VITDET_STAGE_THREADS")) workers = atoi(e) - 1;
+        if (hw > 0 && workers > hw - 1) workers = hw - 1;
+        if (workers < 0) workers = 0;
+        h->stage_pool = new StagePool(workers);
+    }
     const size_t img_bytes = in_bytes / static_cast<size_t>(B);
-    {
-        // the copy stream must not overwrite dev_in while earlier work on `st` may still read it
-        cudaEvent_t e0 = h->copy_events[0];
-        CU_TRY(cudaEventRecord(e0, st));
-        CU_TRY(cudaStreamWaitEvent(h->copy_stream, e0, 0));
-    }
     for (int i = 0; i < n_sub; ++i) {
         const size_t off = static_cast<size_t>(i) * kGran * img_bytes;
         const int cnt = (B - i * kGran) < kGran ? (B - i * kGran) : kGran;
         const size_t bytes = static_cast<size_t>(cnt) * img_bytes;
         const char* src = reinterpret_cast<const char*>(images_host) + off;
         if (!pinned) {
-            memcpy(static_cast<char*>(h->pin_in) + off, src, bytes);
-            src = static_cast<const char*>(h->pin_in) + off;
+            h->stage_pool->copy(static_cast<char*>(sl.pin_in) + off, src, bytes);
+            src = static_cast<const char*>(sl.pin_in) + off;
         }
-        CU_TRY(cudaMemcpyAsync(h->dev_in.as<char>() + off, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-        CU_TRY(cudaEventRecord(h->copy_events[i], h->copy_stream));
+        CU_TRY(cudaMemcpyAsync(sl.dev_in.as<char>() + off, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_TRY(cudaEventRecord(sl.copy_events[i], h->copy_stream));
     }
     ForwardOpts opts;
-    if (B > lead0 + lead1) { opts.lead_chunks[0] = lead0; opts.lead_chunks[1] = lead1; }
-    else if (B > lead0) opts.lead_chunks[0] = lead0;
-    opts.ready = h->copy_events.data();
+    if (lead0 > 0 && B > lead0 + lead1) { opts.lead_chunks[0] = lead0; opts.lead_chunks[1] = lead1; }
+    else if (lead0 > 0 && B > lead0) opts.lead_chunks[0] = lead0;
+    opts.ready = sl.copy_events.data();
     opts.ready_gran = kGran;
     opts.in_u8 = in_u8;
-    char* dbase = h->dev_out.as<char>();
-    vitdet_detections d;
-    d.decoded = reinterpret_cast<float*>(dbase + o_dec);
-    d.class_id = reinterpret_cast<int32_t*>(dbase + o_id);
-    d.class_conf = reinterpret_cast<float*>(dbase + o_cc);
-    d.corners = reinterpret_cast<int32_t*>(dbase + o_cor);
-    d.keep = reinterpret_cast<uint8_t*>(dbase + o_keep);
-    RC_TRY(forward_impl(h, h->dev_in.p, B, mode, reinterpret_cast<float*>(dbase + o_logits), params, &d, st, opts));
-    CU_TRY(cudaMemcpyAsync(h->pin_out, dbase, out_bytes, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    const char* pb = static_cast<const char*>(h->pin_out);
-    if (logits_host) memcpy(logits_host, pb + o_logits, R * 24);
+    char* dbase = sl.dev_out.as<char>();
+    vitdet_detections d = {};
+    d.decoded = reinterpret_cast<float*>(dbase + sl.o_dec);
+    d.class_id = reinterpret_cast<int32_t*>(dbase + sl.o_id);
+    d.class_conf = reinterpret_cast<float*>(dbase + sl.o_cc);
+    d.corners = reinterpret_cast<int32_t*>(dbase + sl.o_cor);
+    d.keep = reinterpret_cast<uint8_t*>(dbase + sl.o_keep);
+    if (want_packed) d.packed = reinterpret_cast<float*>(dbase + sl.o_pk);
+    RC_TRY(forward_impl(h, sl.dev_in.p, B, mode, reinterpret_cast<float*>(dbase), params, &d, st, opts));
+    CU_TRY(cudaMemcpyAsync(sl.pin_out, dbase, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(sl.done, st));
+    sl.busy = true;
+    *ticket = h->next_slot;
+    h->next_slot = (h->next_slot + 1) % vitdet_handle::kHostSlots;
+    return 0;
+}
+
+static int collect_impl(vitdet_handle* h, int ticket, float* logits_host, const vitdet_detections* out_host) {
+    if (!h || ticket < 0 || ticket >= vitdet_handle::kHostSlots) return fail(VITDET_E_INVALID, "collect: bad ticket %d", ticket);
+    HostSlot& sl = h->host_slots[ticket];
+    if (!sl.busy) return fail(VITDET_E_INVALID, "collect: ticket %d is not in flight", ticket);
+    sl.busy = false;
+    CU_TRY(cudaEventSynchronize(sl.done));
+    const char* pb = static_cast<const char*>(sl.pin_out);
+    const size_t R = sl.R;
+    if (logits_host) memcpy(logits_host, pb, R * 24);
     if (out_host) {
-        if (out_host->decoded) memcpy(out_host->decoded, pb + o_dec, R * 24);
-        if (out_host->class_id) memcpy(out_host->class_id, pb + o_id, R * 4);
-        if (out_host->class_conf) memcpy(out_host->class_conf, pb + o_cc, R * 4);
-        if (out_host->corners) memcpy(out_host->corners, pb + o_cor, R * 16);
-        if (out_host->keep) memcpy(out_host->keep, pb + o_keep, R);
+        if (out_host->decoded) memcpy(out_host->decoded, pb + sl.o_dec, R * 24);
+        if (out_host->class_id) memcpy(out_host->class_id, pb + sl.o_id, R * 4);
+        if (out_host->class_conf) memcpy(out_host->class_conf, pb + sl.o_cc, R * 4);
+        if (out_host->corners) memcpy(out_host->corners, pb + sl.o_cor, R * 16);
+        if (out_host->keep) memcpy(out_host->keep, pb + sl.o_keep, R);
+        if (out_host->packed) {
+            if (!sl.has_packed) return fail(VITDET_E_INVALID, "collect: the submission did not ask for packed records");
+            memcpy(out_host->packed, pb + sl.o_pk, R * 52);
+        }
     }
     return 0;
+}
+
+static int predict_host_impl(vitdet_handle* h, const void* images_host, int in_u8, int B, int mode, const vitdet_decode_params* params,
+                             float* logits_host, const vitdet_detections* out_host, void* stream) {
+    int ticket = -1;
+    RC_TRY(submit_host_impl(h, images_host, in_u8, B, mode, params, (out_host && out_host->packed) ? 1 : 0, stream, &ticket));
+    return collect_impl(h, ticket, logits_host, out_host);
 }
 
 extern "C" {
@@ -1315,6 +1430,15 @@ int vitdet_predict_host(vitdet_handle* h, const float* images_host, int B, int m
 int vitdet_predict_host_u8(vitdet_handle* h, const uint8_t* images_host, int B, int mode, const vitdet_decode_params* params,
                            float* logits_host, const vitdet_detections* out_host, void* stream) {
     return predict_host_impl(h, images_host, 1, B, mode, params, logits_host, out_host, stream);
+}
+
+int vitdet_submit_host(vitdet_handle* h, const void* images_host, int images_are_uint8, int B, int mode, const vitdet_decode_params* params,
+                       int want_packed, void* stream, int* ticket) {
+    return submit_host_impl(h, images_host, images_are_uint8 ? 1 : 0, B, mode, params, want_packed, stream, ticket);
+}
+
+int vitdet_collect(vitdet_handle* h, int ticket, float* logits_host, const vitdet_detections* out_host) {
+    return collect_impl(h, ticket, logits_host, out_host);
 }
 
 // ------------------------------------------------------------------------------------------------

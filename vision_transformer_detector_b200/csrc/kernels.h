@@ -114,6 +114,9 @@ int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d);
 cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tcgen05 kernel, one softmax thread per query row (attention_tc.cu)
 cudaError_t attn_tc8_launch(const AttnPlan& plan, cudaStream_t stream);    // tcgen05 kernel, score rows split over warp pairs (attention_tc8.cu)
 cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);   // persistent form of attention_tc.cu (attention_tcp.cu)
+cudaError_t attn_sw_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent, software-pipelined softmax warps (attention_sw.cu)
+cudaError_t attn_pp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent ping-pong: two work streams per CTA take turns on the SFU (attention_pp.cu)
+cudaError_t attn_tc8p_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);  // persistent + split score rows (attention_tc8p.cu)
 cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -152,6 +155,7 @@ struct DecodeOut {
     float* class_conf = nullptr;  // [R] (0.5 - |class - id|) / 0.5
     uint8_t* keep = nullptr;    // [R]
     int32_t* corners = nullptr; // [R, 4] x0, y0, x1, y1 (int truncation then clip; det.py:2300-2325), optional
+    float* packed = nullptr;    // [R, 13] decoded[6] | class id | class confidence | keep | corners[4], all as float32 (the gather record)
 };
 cudaError_t head_tail_launch(const void* h, int ldh, int in_f32, const float* w /*[6, U] f32*/, const float* bias,
                              int R, int U, const DecodeParams& dp, const DecodeOut& out, cudaStream_t stream);

@@ -253,17 +253,24 @@ __device__ __forceinline__ void decode_slot(const float (&l)[6], long long r, co
     if (o.class_id) o.class_id[r] = static_cast<int32_t>(id);
     if (o.class_conf) o.class_conf[r] = cc;
     if (o.keep) o.keep[r] = keep ? 1 : 0;
-    if (o.corners) {
+    if (o.corners || o.packed) {
         // det.py:2300-2325: int() truncation toward zero, then clip to the image.
         // boxes are scaled by enlarged_image_scale first (det.py:2294-2297); the clip bounds are the enlarged image's
         // width / height, round(size * scale) (det.py:2237-2252)
         const float s = dp.corner_scale;
         const int iw = static_cast<int>(rintf(dp.img_w * s)), ih = static_cast<int>(rintf(dp.img_h * s));
         const float cx = dec[2] * s, cy = dec[3] * s, bh = dec[4] * s, bw = dec[5] * s;
-        o.corners[r * 4 + 0] = clip_int(static_cast<int>(cx - bw / 2.f), 0, iw);
-        o.corners[r * 4 + 1] = clip_int(static_cast<int>(cy - bh / 2.f), 0, ih);
-        o.corners[r * 4 + 2] = clip_int(static_cast<int>(cx + bw / 2.f), 0, iw);
-        o.corners[r * 4 + 3] = clip_int(static_cast<int>(cy + bh / 2.f), 0, ih);
+        const int c0 = clip_int(static_cast<int>(cx - bw / 2.f), 0, iw), c1 = clip_int(static_cast<int>(cy - bh / 2.f), 0, ih);
+        const int c2 = clip_int(static_cast<int>(cx + bw / 2.f), 0, iw), c3 = clip_int(static_cast<int>(cy + bh / 2.f), 0, ih);
+        if (o.corners) { o.corners[r * 4 + 0] = c0; o.corners[r * 4 + 1] = c1; o.corners[r * 4 + 2] = c2; o.corners[r * 4 + 3] = c3; }
+        if (o.packed) {
+            // the fixed-size record the ranks all-gather: ints are exact in float32 (< 2^24)
+            float* pk = o.packed + r * 13;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) pk[j] = dec[j];
+            pk[6] = id; pk[7] = cc; pk[8] = keep ? 1.f : 0.f;
+            pk[9] = static_cast<float>(c0); pk[10] = static_cast<float>(c1); pk[11] = static_cast<float>(c2); pk[12] = static_cast<float>(c3);
+        }
     }
 }
 

@@ -43,6 +43,50 @@ def unpack_records(packed, slots: int = 17) -> dict:
             "corners": packed[:, 9:13].astype(np.int32).reshape(n, slots, 4)}
 
 
+class RecordGather:
+    """The C-ABI form of the exchange: vitdet_gather_detections (csrc/gather.cu) on a NCCL communicator that the library
+    creates itself — rank 0 draws the unique id, torch.distributed (any backend) broadcasts its 128 bytes.  With the
+    packed record written by the head-tail kernel (model.detect(..., packed=True)) the timed multi-GPU step contains no
+    eager PyTorch kernel."""
+
+    def __init__(self, device):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _capi
+        self._lib = _capi.load()
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _capi.check(self._lib.vitdet_nccl_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().tolist())
+        self._comm = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(self._lib.vitdet_nccl_comm_create(uid, self.rank, self.world, C.byref(self._comm)))
+
+    def all_gather(self, packed):
+        """packed: float32 CUDA tensor [rows, 13] of this rank -> [world * rows, 13] in rank order (asynchronous on
+        torch's current stream)."""
+        import ctypes as C
+        import torch
+        from . import _capi
+        packed = packed.contiguous()
+        out = torch.empty((self.world * packed.shape[0], packed.shape[1]), dtype=torch.float32, device=packed.device)
+        with torch.cuda.device(packed.device):
+            _capi.check(self._lib.vitdet_gather_detections(self._comm, C.c_void_p(packed.data_ptr()), int(packed.shape[0]),
+                                                           C.c_void_p(out.data_ptr()),
+                                                           C.c_void_p(torch.cuda.current_stream(packed.device).cuda_stream)))
+        return out
+
+    def close(self):
+        if getattr(self, "_comm", None) is not None and self._comm:
+            self._lib.vitdet_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
 def all_gather_records(packed):
     """All-gathers equally sized packed record blocks of every rank, in rank order (one collective)."""
     import torch

@@ -223,6 +223,7 @@ class DetectionRecords:
     class_conf: Any    # (B,17)   f32 (0.5 - |class - id|) / 0.5
     keep: Any          # (B,17)   u8  both thresholds passed
     corners: Any       # (B,17,4) i32 x0, y0, x1, y1
+    packed: Any = None  # (B*17,13) f32 the same record as one row (what the ranks all-gather); only with packed=True
 
     def detections(self) -> list[list[dict]]:
         """Kept slots per image as plain records (what the visualise loop iterates, det.py:2260-2325)."""
@@ -284,10 +285,12 @@ def _alloc_records_torch(B: int, S: int, device):
             torch.empty((B, S, 4), dtype=torch.int32, device=device))
 
 
-def _records_struct(decoded, class_id, class_conf, keep, corners) -> _capi.Detections:
+def _records_struct(decoded, class_id, class_conf, keep, corners, packed=None) -> _capi.Detections:
     ptr = (lambda a: C.c_void_p(a.data_ptr())) if hasattr(decoded, "data_ptr") else _capi.np_ptr
     d = _capi.Detections()
     d.decoded, d.class_id, d.class_conf, d.keep, d.corners = ptr(decoded), ptr(class_id), ptr(class_conf), ptr(keep), ptr(corners)
+    if packed is not None:
+        d.packed = ptr(packed)
     return d
 
 
@@ -682,9 +685,10 @@ class VisionTransformerDetector:
         return int(shape[0])
 
     def detect(self, x, objectness_threshold=None, classification_threshold=None, strict=True, image_size=None,
-               compute_mode: str | None = None) -> DetectionRecords:
+               compute_mode: str | None = None, packed: bool = False) -> DetectionRecords:
         """predict + transform_predictions + thresholds in one call (the decode is fused into the
-        head's last Dense).  image_size defaults to the model's own input size."""
+        head's last Dense).  image_size defaults to the model's own input size.  packed=True also returns the
+        (B*17, 13) float32 record block that the multi-GPU gather exchanges (parallel.RECORD_WIDTH)."""
         B = self._check_images(x.shape)
         S = Constants.MAX_DETECT_OBJECTS_QUANTITY.value
         if image_size is None:
@@ -697,7 +701,8 @@ class VisionTransformerDetector:
             xi = x.contiguous() if u8 else x.to(torch.float32).contiguous()
             with torch.cuda.device(xi.device):
                 logits, dec, cid, cc, keep, cor = _alloc_records_torch(B, S, xi.device)
-                st = _records_struct(dec, cid, cc, keep, cor)
+                pk = torch.empty((B * S, 13), dtype=torch.float32, device=xi.device) if packed else None
+                st = _records_struct(dec, cid, cc, keep, cor, pk)
                 if u8:
                     _capi.check(self._lib.vitdet_forward_u8(self._h, C.c_void_p(xi.data_ptr()), B, C.c_void_p(logits.data_ptr()), mode,
                                                             C.byref(params), C.byref(st), _torch_stream_ptr(xi.device)))
@@ -705,13 +710,42 @@ class VisionTransformerDetector:
                     _capi.check(self._lib.vitdet_forward_decode(self._h, C.c_void_p(xi.data_ptr()), B, mode, C.byref(params),
                                                                 C.c_void_p(logits.data_ptr()), C.byref(st),
                                                                 _torch_stream_ptr(xi.device)))
-            return DetectionRecords(logits, dec, cid, cc, keep, cor)
+            return DetectionRecords(logits, dec, cid, cc, keep, cor, pk)
         xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         logits, dec, cid, cc, keep, cor = _alloc_records_np(B, S)
-        st = _records_struct(dec, cid, cc, keep, cor)
+        pk = np.empty((B * S, 13), np.float32) if packed else None
+        st = _records_struct(dec, cid, cc, keep, cor, pk)
         fn = self._lib.vitdet_predict_host_u8 if u8 else self._lib.vitdet_predict_host
         _capi.check(fn(self._h, _capi.np_ptr(xi), B, mode, C.byref(params), _capi.np_ptr(logits), C.byref(st), None))
-        return DetectionRecords(logits, dec, cid, cc, keep, cor)
+        return DetectionRecords(logits, dec, cid, cc, keep, cor, pk)
+
+    def submit(self, x, objectness_threshold=None, classification_threshold=None, strict=True, image_size=None,
+               compute_mode: str | None = None, packed: bool = False) -> int:
+        """Asynchronous detect() for HOST arrays (vitdet_submit_host): stages and copies `x`, enqueues forward + decode +
+        read-back and returns a ticket for collect().  Two submissions may be in flight; the copy of the second overlaps
+        the compute of the first.  A page-locked `x` must stay alive until its ticket is collected."""
+        B = self._check_images(np.shape(x))
+        if image_size is None:
+            image_size = self.config.input_shape[:2]
+        params = _decode_params(objectness_threshold, classification_threshold, strict, image_size)
+        u8 = _is_uint8(x)
+        xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        ticket = C.c_int(-1)
+        _capi.check(self._lib.vitdet_submit_host(self._h, _capi.np_ptr(xi), 1 if u8 else 0, B, self._mode(compute_mode), C.byref(params),
+                                                 1 if packed else 0, None, C.byref(ticket)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[ticket.value] = (B, packed, xi)          # xi kept alive: a page-locked buffer is read asynchronously
+        return ticket.value
+
+    def collect(self, ticket: int) -> DetectionRecords:
+        """Waits for a submit() ticket and returns its records as numpy arrays."""
+        B, packed, _ = self._inflight.pop(ticket)
+        S = Constants.MAX_DETECT_OBJECTS_QUANTITY.value
+        logits, dec, cid, cc, keep, cor = _alloc_records_np(B, S)
+        pk = np.empty((B * S, 13), np.float32) if packed else None
+        st = _records_struct(dec, cid, cc, keep, cor, pk)
+        _capi.check(self._lib.vitdet_collect(self._h, int(ticket), _capi.np_ptr(logits), C.byref(st)))
+        return DetectionRecords(logits, dec, cid, cc, keep, cor, pk)
 
     def predict(self, x, batch_size=None, verbose="auto", steps=None, callbacks=None, **kwargs):
         """keras Model.predict: host array in, numpy (B, 17, 6) raw logits out.  `batch_size` only
