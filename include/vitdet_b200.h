@@ -46,7 +46,10 @@ enum {
 /* Arithmetic mode of the forward pass.
  *   BF16: bf16 operands on the tcgen05 tensor cores, f32 accumulation, f32 residual stream,
  *         LayerNorm / softmax statistics in f32  (tolerance vs the f64 oracle: 2e-2).
- *   FP32: every product and sum in IEEE f32, as the reference computes (tolerance 1e-3). */
+ *   FP32: the fp32-accumulate mode (tolerance 1e-3): float32 activations and statistics; by default the Dense layers
+ *         run on the tensor cores with every operand split into two bf16 planes (hi + lo, 16 significant bits) and
+ *         three tcgen05 passes per product (hi*hi + hi*lo + lo*hi, float32 accumulation, exact activations);
+ *         vitdet_set_option(h, "fp32_tc", 0) selects IEEE float32 FMA kernels for every product instead. */
 enum { VITDET_MODE_BF16 = 0, VITDET_MODE_FP32 = 1 };
 
 /* Keyword arguments of create_vision_transformer_detector (det.py:498-506) plus the module
@@ -120,6 +123,8 @@ int64_t vitdet_launch_count(vitdet_handle* h, int reset);
  *   "fuse_ln"    1 (default): LayerNorm runs in the epilogue of the GEMM that produces the residual-stream row; 0: stand-alone kernel
  *   "fuse_tail"  1 (default): the last three MLP layers of a block run as one kernel; 0: three GEMM launches
  *   "gemm_pair"  1 (default): CTA-pair GEMM for K >= 512 layers; 0: never; 2: wherever it is legal
+ *   "fp32_tc"    1 (default): the fp32 mode's Dense layers run on the tensor cores as three-pass split-bf16 products with
+ *                float32 accumulation; 0: IEEE float32 FMA kernels on the CUDA cores (the strict reference form)
  *   "attention"  40 (default): persistent kernel (attention_tcp.cu); 4: one CTA per 128-query work item (attention_tc.cu);
  *                8: score rows split over warp pairs (attention_tc8.cu) */
 int vitdet_set_option(vitdet_handle* h, const char* key, int value);

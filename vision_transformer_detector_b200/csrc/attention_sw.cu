@@ -213,7 +213,9 @@ attn_sw_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnSwArgs p) {
         uint32_t kphase = 0, vphase = 0;
         int jq = 0, itq = 0;        // (tile within item, item ordinal) of the next QK^T
         int jp = 0;                 // tile within item of the next PV
-        for (int g = 0; g <= total; ++g) {
+        // Step g issues QK^T(g) and then PV(g-2): the softmax warps release S(g-1) and publish P(g-2) at the same moment
+        // (the end of their tile g-2), and the scores are needed first.
+        for (int g = 0; g <= total + 1; ++g) {
             if (g < total) {
                 const int qb = itq & 1;
                 if (jq == 0) {
@@ -251,10 +253,10 @@ attn_sw_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnSwArgs p) {
                 if (++ks == kKSlots) { ks = 0; kphase ^= 1u; }
                 if (++jq == nkv) { jq = 0; ++itq; }
             }
-            if (g > 0) {
-                // O (+)= P(g-1) V(g-1)
+            if (g > 1) {
+                // O (+)= P(g-2) V(g-2)
                 mbar_wait(bar_vfull + 8 * vs, vphase);
-                mbar_wait(bar_p_full, (g - 1) & 1);
+                mbar_wait(bar_p_full, (g - 2) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t dv = dv0 + static_cast<uint64_t>(vs * kSlotStep);

@@ -1,0 +1,349 @@
+// Multi-head self-attention core, THREE CTAs per SM: softmax(q k^T / sqrt(d)) v per (image, head) on tcgen05
+// (keras.layers.MultiHeadAttention, reference det.py:364-369).
+//
+// Measured in profiles/r02_attention_analysis.md: one warp gets at most one warp-wide ex2 every ~16 clocks while the SFU
+// of its sub-partition takes one every 8, so the SFU is only busy while at least two softmax warps per sub-partition are
+// inside their exponential phase; attention_tc.cu has exactly two (two CTAs per SM: 512 TMEM columns / 256).  This
+// variant trades tile size for residency: 64-key tiles need S 64 | O 64 columns (one 128-column allocation) + P 32 (a
+// second allocation) = 160 columns, so three CTAs share an SM (480 columns, 3 x 64 KB of shared memory, 112 registers
+// per thread) and every sub-partition has three softmax warps.
+#include <cstdlib>
+#include "common.cuh"
+#include "kernels.h"
+#include "launch.h"
+
+namespace vitdet {
+
+namespace {
+
+constexpr int kQ = 128;            // queries per CTA (UMMA M)
+constexpr int kKV = 64;            // keys per tile (UMMA N of QK^T, K of PV)
+constexpr int kHP = 64;            // head pitch in elements (one 128-byte swizzle row of bf16)
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+// softmax warps 0..3 (warp = TMEM lane quadrant); the TMA producer and the MMA issuer take the highest warp ids,
+// which the warp arbiter favours: the MMA issuer's wake-up latency is on the critical path of every tile
+constexpr int kProducerWarp = 4, kMmaWarp = 5;
+constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
+constexpr int kTileBytes = kKV * kHP * 2;     // 8 KiB: one K tile or one V tile = one TMA box of 64 rows
+constexpr int kBoxBytes = 64 * kHP * 2;
+constexpr int kTmemColsA = 128, kTmemColsB = 32;
+constexpr uint32_t kColS = 0, kColO = 64;   // allocation A: S [0,64) f32 | O [64,128) f32; allocation B: P [0,32) bf16x2
+constexpr float kRescaleThreshold = 8.f;      // log2 units: P stays <= 2^8 between rescales
+
+struct AttnTc3Args {
+    __nv_bfloat16* ctx;
+    int ldo;
+    int T, H;
+    int hp;              // elements per head in qkv / ctx (key_dim rounded up to 8)
+    int k16;             // ceil(d / 16): K steps of the QK^T product
+    float scale_log2;    // log2(e) / sqrt(key_dim)
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that
+// hold at least one existing key (4 for a full tile), MASK = the last of them is partial.  Static loops only,
+// so that the 128 scores stay in registers.
+template <int NCH, bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t tO, uint32_t bar_s_free, uint32_t bar_pv_done,
+                                             uint32_t bar_p_full, int lane, int j, int valid, float scale_log2,
+                                             float& m_used, float& l) {
+    // the row slice into registers (all loads in flight, one wait), then S belongs to the MMA warp again and
+    // QK^T(j+1) overlaps this tile's softmax
+    uint32_t v[NCH][32];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld_32x32(tS + 32u * c, v[c]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_s_free);
+
+    if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (32 * (NCH - 1) + i >= valid) v[NCH - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
+    }
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            mx[0] = fmaxf(mx[0], __uint_as_float(v[c][i]));     mx[1] = fmaxf(mx[1], __uint_as_float(v[c][i + 1]));
+            mx[2] = fmaxf(mx[2], __uint_as_float(v[c][i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(v[c][i + 3]));
+        }
+    const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2);
+    const bool grow = __any_sync(0xffffffffu, m_new > m_used + kRescaleThreshold);   // true on the first tile
+    float alpha = 1.f;
+    if (grow) {
+        alpha = ex2f(m_used - m_new);       // 0 on the first tile (m_used = -inf)
+        m_used = m_new;
+        l *= alpha;
+    }
+    const float neg_m = -m_used;
+    // p = 2^(s*c - m) in place; packed pairs overwrite the first half of each chunk's registers.  The scale-and-shift
+    // and the row sums run on packed float pairs (FFMA2 / FADD2: one issue slot for two elements).
+    const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(neg_m, neg_m);
+    uint64_t sum2[2] = {0ull, 0ull};       // two (0.f, 0.f) pairs
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float t0, t1, t2, t3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), t0, t1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])), sc2, nm2), t2, t3);
+            const float e0 = ex2f(t0), e1 = ex2f(t1), e2 = ex2f(t2), e3 = ex2f(t3);      // ex2(-inf) = 0
+            sum2[0] = f2_add(sum2[0], f2_pack(e0, e1));
+            sum2[1] = f2_add(sum2[1], f2_pack(e2, e3));
+            v[c][i / 2] = pack_bf16x2(e0, e1);
+            v[c][i / 2 + 1] = pack_bf16x2(e2, e3);
+        }
+    {
+        float s0, s1, s2, s3;
+        f2_unpack(sum2[0], s0, s1);
+        f2_unpack(sum2[1], s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+    }
+
+    // P and O must no longer be in use by PV(j-1)
+    if (j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (grow) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(tO + 32u * c, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32_x32(tO + 32u * c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kKV / 32; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = (c < NCH) ? v[c < NCH ? c : 0][i] : 0u;     // P = 0 for keys that do not exist
+        tmem_st_32x32_x16(tP + 16u * c, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p_full);
+}
+
+__global__ void __maxnreg__(112)
+attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTc3Args p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 5];
+    __shared__ uint32_t tmem_base_s, tmem_base_p;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const int q0 = blockIdx.x * kQ;
+    const int bh = blockIdx.y;
+    const int b = bh / p.H, h = bh - b * p.H;
+    const int row_base = b * p.T;          // first token row of this image in the [B*T, ld] matrices
+    const int nkv = (p.T + kKV - 1) / kKV;
+
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0u) __trap();
+    const uint32_t sQ = base;
+    const uint32_t sKV = base + kQBytes;               // stage s: K at + 2*s*tile, V right after
+    const uint32_t bar_full = smem_u32(&bars[0]);
+    const uint32_t bar_empty = smem_u32(&bars[kStages]);
+    const uint32_t bar_q = smem_u32(&bars[2 * kStages]);
+    const uint32_t bar_s_full = smem_u32(&bars[2 * kStages + 1]);   // QK^T(j) complete                 (MMA commit)
+    const uint32_t bar_s_free = smem_u32(&bars[2 * kStages + 2]);   // S(j) is in registers             (4 warps)
+    const uint32_t bar_p_full = smem_u32(&bars[2 * kStages + 3]);   // P(j) (and rescaled O) in TMEM    (4 warps)
+    const uint32_t bar_pv_done = smem_u32(&bars[2 * kStages + 4]);  // PV(j) complete                   (MMA commit)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_q, 1);
+        mbar_init(bar_s_full, 1);
+        mbar_init(bar_s_free, 4);
+        mbar_init(bar_p_full, 4);
+        mbar_init(bar_pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&tmem_base_s), kTmemColsA);
+        tmem_alloc(smem_u32(&tmem_base_p), kTmemColsB);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s, tmem_p = tmem_base_p;
+    pdl_wait();       // set-up above overlapped the previous kernel; q/k/v are read from here on
+
+    if (warp == kProducerWarp) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQKV);
+            mbar_arrive_expect_tx(bar_q, kQBytes);
+            tma_load_2d(sQ, &tmQKV, bar_q, h * p.hp, row_base + q0);
+            tma_load_2d(sQ + kBoxBytes, &tmQKV, bar_q, h * p.hp, row_base + q0 + 64);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < nkv; ++j) {
+                mbar_wait_relaxed(bar_empty + 8 * stage, phase ^ 1u);
+                mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kTileBytes);
+                const uint32_t dK = sKV + stage * 2 * kTileBytes;
+                const int r = row_base + j * kKV;
+                tma_load_2d(dK, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp, r);
+                tma_load_2d(dK + kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp, r);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------ MMA issuer --------------------------------
+        // The whole warp runs the loop (warp-uniform control flow, loop state in uniform registers); only the
+        // tcgen05 instructions are issued by one elected lane.  Its wake-up-to-issue latency is on the critical
+        // path of every tile.
+        const uint32_t idesc_qk = umma_idesc_bf16_f32(kQ, kKV);
+        const uint32_t idesc_pv = umma_idesc_bf16_f32_bmn(kQ, 16 * p.k16);
+        const uint32_t tS = tmem_base + kColS, tP = tmem_p, tO = tmem_base + kColO;
+        const uint64_t dq = umma_desc_sw128_kmajor(sQ);
+        const uint64_t dkv0 = umma_desc_sw128_kmajor(sKV);
+        constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4, kVOff = kTileBytes >> 4;     // descriptor address units (16 B)
+        mbar_wait(bar_q, 0);
+        // Heads are stored hp (< 64) columns apart, so the 64-column TMA boxes also carry the first columns of the
+        // next head.  In QK^T only the columns below 16 * k16 take part: clearing Q's columns [hp, 16 * k16) once makes
+        // their products vanish whatever K holds there; V's extra columns only produce columns of O that are never
+        // stored.  16-byte chunk c of row r sits at chunk c ^ (r & 7) of the 128-byte swizzled row.
+        if (p.hp < 16 * p.k16) {
+            const int c_lo = p.hp >> 3, c_hi = 2 * p.k16;
+            for (int r = lane; r < kQ; r += 32)
+                for (int c = c_lo; c < c_hi; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + r * 128 + ((c ^ (r & 7)) << 4)), "r"(0u) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j <= nkv; ++j) {
+            if (j < nkv) {
+                // S = Q K(j)^T; the softmax warps moved S(j-1) into registers before signalling s_free
+                mbar_wait(bar_full + 8 * stage, phase);
+                if (j >= 1) mbar_wait(bar_s_free, (j - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dk = dkv0 + static_cast<uint64_t>(stage * kStageStep);
+                    umma_bf16_ss(tS, dq, dk, idesc_qk, 0u);
+                    if (p.k16 > 1) umma_bf16_ss(tS, dq + 2u, dk + 2u, idesc_qk, 1u);
+                    if (p.k16 > 2) umma_bf16_ss(tS, dq + 4u, dk + 4u, idesc_qk, 1u);
+                    if (p.k16 > 3) umma_bf16_ss(tS, dq + 6u, dk + 6u, idesc_qk, 1u);
+                    umma_commit(bar_s_full);
+                }
+                __syncwarp();
+            }
+            if (j > 0) {
+                // O += P(j-1) V(j-1)
+                const int ps = (j - 1) % kStages;
+                mbar_wait(bar_p_full, (j - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dv = dkv0 + static_cast<uint64_t>(ps * kStageStep + kVOff);
+                    // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+#pragma unroll
+                    for (int k = 0; k < kKV / 16; ++k)
+                        umma_bf16_ts(tO, tP + 8u * k, dv + static_cast<uint64_t>(128u * k), idesc_pv, (k != 0) ? 1u : (j > 1 ? 1u : 0u));
+                    umma_commit(bar_empty + 8 * ps);
+                    umma_commit(bar_pv_done);
+                }
+                __syncwarp();
+            }
+            if (j < nkv) { if (++stage == kStages) { stage = 0; phase ^= 1u; } }
+        }
+    } else {
+        // ------------------------------ softmax -----------------------------------
+        const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t tP = tmem_p + lane_off, tO = tmem_base + lane_off + kColO;
+        float m_used = -INFINITY;      // running maximum in the scaled log2 domain
+        float l = 0.f;                 // running sum of p
+        const uint32_t tS = tmem_base + lane_off + kColS;
+        for (int j = 0; j < nkv; ++j) {
+            const int valid = min(kKV, p.T - j * kKV);      // keys of this tile that exist
+            mbar_wait(bar_s_full, j & 1);
+            tc_fence_after();
+#define VITDET_TILE(NCH, MASK) \
+    softmax_tile<NCH, MASK>(tS, tP, tO, bar_s_free, bar_pv_done, bar_p_full, lane, j, valid, p.scale_log2, m_used, l)
+            if (valid == kKV) {
+                VITDET_TILE(2, false);
+            } else {
+                // last tile of the image: only the chunks with existing keys are loaded and exponentiated; warp-uniform dispatch
+                const bool partial = (valid & 31) != 0;
+                if (valid <= 32) { if (partial) VITDET_TILE(1, true); else VITDET_TILE(1, false); }
+                else VITDET_TILE(2, true);
+            }
+#undef VITDET_TILE
+        }
+
+        // ---- finalise: O / l -> bf16 context rows ----
+        mbar_wait(bar_pv_done, (nkv - 1) & 1);
+        tc_fence_after();
+        const int q = q0 + quad * 32 + lane;
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.ctx + static_cast<size_t>(row_base + (q < p.T ? q : 0)) * p.ldo + h * p.hp;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + 32u * c, o);
+            tmem_ld_wait();
+            if (q < p.T) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (32 * c + 8 * g >= p.hp) break;          // the head holds hp columns; O's further columns are zero
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + 32 * c + 8 * g) = w;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemColsA);
+        tmem_dealloc(tmem_p, kTmemColsB);
+    }
+}
+
+}  // namespace
+
+cudaError_t attn_tc3_launch(const AttnPlan& plan, cudaStream_t stream) {
+    const AttnDesc& d = plan.desc;
+    AttnTc3Args a;
+    a.ctx = static_cast<__nv_bfloat16*>(d.ctx);
+    a.ldo = d.ldo;
+    a.T = d.T;
+    a.H = d.H;
+    a.hp = d.hp;
+    a.k16 = (d.d + 15) / 16;
+    a.scale_log2 = d.scale * 1.4426950408889634f;
+    const size_t smem = static_cast<size_t>(kQBytes) + static_cast<size_t>(kStages) * 2 * kTileBytes;
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc3_kernel), static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    dim3 grid((d.T + kQ - 1) / kQ, d.B * d.H);
+    return launch_kernel(attn_tc3_kernel, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
+}
+
+}  // namespace vitdet

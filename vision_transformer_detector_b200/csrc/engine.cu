@@ -65,7 +65,8 @@ struct Options {
     int fuse_ln = 1;       // VITDET_FUSE_LN=0: stand-alone LayerNorm kernel
     int fuse_tail = 1;     // VITDET_FUSE_TAIL=0: the last three MLP layers as separate GEMM launches
     int gemm_pair = 1;     // VITDET_GEMM_PAIR=0 never / all (2) wherever legal / default: K >= 512 layers
-    int attention = 40;    // VITDET_ATTN: 40 persistent kernel (attention_tcp.cu), 4 one CTA per work item (attention_tc.cu), 8 split score rows (attention_tc8.cu)
+    int fp32_tc = 1;       // VITDET_FP32=simt: the fp32 mode on CUDA-core IEEE kernels instead of split-bf16 tensor-core GEMMs
+    int attention = 4;     // VITDET_ATTN: 4 one CTA per work item (attention_tc.cu, the fastest measured); experimental forms: 40 persistent, 8 / 80 split score rows, 2 ping-pong, 1 software-pipelined, 3 three CTAs per SM
 };
 
 static Options env_options() {
@@ -73,7 +74,8 @@ static Options env_options() {
     if (const char* e = getenv("VITDET_FUSE_LN")) o.fuse_ln = strcmp(e, "0") != 0;
     if (const char* e = getenv("VITDET_FUSE_TAIL")) o.fuse_tail = strcmp(e, "0") != 0;
     if (const char* e = getenv("VITDET_GEMM_PAIR")) o.gemm_pair = strcmp(e, "0") == 0 ? 0 : (strcmp(e, "all") == 0 ? 2 : 1);
-    if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 40 || v == 80) o.attention = v; }
+    if (const char* e = getenv("VITDET_FP32")) o.fp32_tc = strcmp(e, "simt") != 0;
+    if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8 || v == 40 || v == 80) o.attention = v; }
     return o;
 }
 
@@ -83,6 +85,7 @@ static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, c
     if (version == 80) return attn_tc8p_launch(plan, num_sms, st);
     if (version == 2) return attn_pp_launch(plan, num_sms, st);
     if (version == 1) return attn_sw_launch(plan, num_sms, st);
+    if (version == 3) return attn_tc3_launch(plan, st);
     return attn_tcp_launch(plan, num_sms, st);
 }
 
@@ -95,15 +98,20 @@ static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, c
 // (identity for plain Dense; gn = key_dim, pn = 64 scatters the heads of a q/k/v kernel to their
 // 64-wide slots; gk = key_dim, pk = 64 does the same for the K axis of attention_output).
 __global__ void pack_dense_kernel(const float* __restrict__ src, int K, int N, int gn, int pn, int row_off, int gk,
-                                  int pk, __nv_bfloat16* __restrict__ w16, int ld16, float* __restrict__ w32,
-                                  int ld32) {
+                                  int pk, __nv_bfloat16* __restrict__ w16, int ld16, long long lo_off,
+                                  float* __restrict__ w32, int ld32) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(K) * N) return;
     const int k = static_cast<int>(idx / N), n = static_cast<int>(idx - static_cast<long long>(k) * N);
     const int r = row_off + (n / gn) * pn + n % gn;
     const int c = (k / gk) * pk + k % gk;
     const float v = src[idx];
-    if (w16) w16[static_cast<size_t>(r) * ld16 + c] = __float2bfloat16_rn(v);
+    if (w16) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        w16[static_cast<size_t>(r) * ld16 + c] = hi;
+        // lo plane of the split (fp32-accumulate) form: v = hi + lo up to 2^-18 |v|
+        if (lo_off) w16[lo_off + static_cast<size_t>(r) * ld16 + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
     if (w32) w32[static_cast<size_t>(r) * ld32 + c] = v;
 }
 
@@ -119,6 +127,31 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int rows, int 
     if (idx >= static_cast<long long>(rows) * ldd) return;
     const int r = static_cast<int>(idx / ldd), c = static_cast<int>(idx - static_cast<long long>(r) * ldd);
     dst[idx] = __float2bfloat16_rn(c < cols ? src[static_cast<size_t>(r) * lds + c] : 0.f);
+}
+
+// float32 rows -> the split (hi, lo) bf16 planes of the fp32-accumulate mode: hi = bf16(x), lo = bf16(x - hi); columns
+// [cols, ldd) are written as zero.  8 elements per thread, 16-byte stores.
+__global__ void split_rows_kernel(const float* __restrict__ src, long long rows, int cols, int lds, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int ldd) {
+    const int vec_per_row = ldd >> 3;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= rows * vec_per_row) return;
+    const long long r = idx / vec_per_row;
+    const int c0 = static_cast<int>(idx - r * vec_per_row) << 3;
+    const float* s = src + r * lds + c0;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (c0 + i < cols) ? s[i] : 0.f;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - __low2float(hh), x[2 * i + 1] - __high2float(hh));
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldd + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + r * ldd + c0) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __global__ void pad_rows_f32_kernel(const float* __restrict__ src, int rows, int cols, int lds, float* __restrict__ dst,
@@ -169,6 +202,18 @@ __global__ void unpack_ctx_kernel(const T* __restrict__ ctx, long long rows, int
     out[idx] = val;
 }
 
+// context rows kept as (hi, lo) bf16 planes [rows, H*hp] -> float32 [rows, H, d]
+__global__ void unpack_ctx_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long rows, int H,
+                                         int d, int hp, float* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= rows * H * d) return;
+    const long long r = idx / (H * d);
+    const int c = static_cast<int>(idx - r * (H * d));
+    const int hh = c / d, j = c - hh * d;
+    const long long o = r * (H * hp) + hh * hp + j;
+    out[idx] = __bfloat162float(hi[o]) + __bfloat162float(lo[o]);
+}
+
 static inline int blocks_for(long long n, int bs = 256) { return static_cast<int>((n + bs - 1) / bs); }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,12 +223,14 @@ static inline int blocks_for(long long n, int bs = 256) { return static_cast<int
 struct DenseW {
     int N = 0, K = 0;          // packed GEMM shape (N includes head-slot pads for qkv, K for attention_output)
     int ld16 = 0, ld32 = 0;
-    DevBuf w16, w32, bias;     // bias: f32 [round_up(N, 8)]
+    DevBuf w16, w32, bias;     // w16: hi plane [N, ld16] followed by the lo plane (split form); bias: f32 [round_up(N, 8)]
+    long long lo_off() const { return static_cast<long long>(N) * ld16; }
+    const void* w16_lo() const { return w16.as<__nv_bfloat16>() + lo_off(); }
     int alloc(int n, int k) {
         N = n; K = k;
         ld16 = round_up(k, 8);
         ld32 = round_up(k, 4);
-        RC_TRY(w16.ensure(static_cast<size_t>(n) * ld16 * 2));
+        RC_TRY(w16.ensure(static_cast<size_t>(n) * ld16 * 2 * 2));
         RC_TRY(w32.ensure(static_cast<size_t>(n) * ld32 * 4));
         RC_TRY(bias.ensure(static_cast<size_t>(round_up(n, 8)) * 4));
         CU_TRY(cudaMemset(w16.p, 0, w16.bytes));
@@ -311,6 +358,7 @@ struct vitdet_handle {
 
     // workspace (grow-only)
     DevBuf x, patch, y, qkv, ctx, u0, u1, s, h0, h1;
+    DevBuf tmp32;                       // fp32 tensor-core mode: float32 staging of the patches / LayerNorm rows before their split, planes of the slot matrix
     // cached plans
     struct EncPlans {
         bool valid = false;
@@ -327,6 +375,7 @@ struct vitdet_handle {
         std::vector<TcGemmPlan> dense;
     };
     std::map<int, HeadPlans> head_plans;    // key: batch
+    std::map<long long, std::vector<TcGemmPlan>> plans32;    // fp32-accumulate mode on the tensor cores: GEMM plans in launch order, key (B << 20) | chunk
 
     // debug taps (vitdet_debug_taps): residual stream after the patch embedding and after every block, of the last forward
     int s_layout_mode = -1;             // arithmetic mode the slot matrix `s` was last laid out for (its pad columns are zeroed per layout)
@@ -606,13 +655,16 @@ static int ensure_workspace(vitdet_handle* h, int B, int mode) {
     const size_t bc = static_cast<size_t>(B < h->chunk ? B : h->chunk);
     const size_t Mc = bc * h->T, R = static_cast<size_t>(B) * h->S;
     const void* before[10] = {h->x.p, h->patch.p, h->y.p, h->qkv.p, h->ctx.p, h->u0.p, h->u1.p, h->s.p, h->h0.p, h->h1.p};
+    // + kPlaneSlack: in the fp32 tensor-core mode a buffer holds two bf16 planes, the second one at the 256-byte
+    // boundary below the middle of the allocation (planes_of); the slack keeps that boundary above the first plane
+    constexpr size_t kPlaneSlack = 1024;
     RC_TRY(h->x.ensure(static_cast<size_t>(B) * h->T * m.D4 * 4));
-    RC_TRY(h->patch.ensure(Mc * m.Pld * m.es));
-    RC_TRY(h->y.ensure(Mc * m.D8 * m.es));
-    RC_TRY(h->qkv.ensure(Mc * m.w_qkv * m.es));
-    RC_TRY(h->ctx.ensure(Mc * m.w_ctx * m.es));
-    RC_TRY(h->u0.ensure(Mc * m.w_u0 * m.es));
-    RC_TRY(h->u1.ensure(Mc * m.w_u1 * m.es));
+    RC_TRY(h->patch.ensure(Mc * m.Pld * m.es + kPlaneSlack));
+    RC_TRY(h->y.ensure(Mc * m.D8 * m.es + kPlaneSlack));
+    RC_TRY(h->qkv.ensure(Mc * m.w_qkv * m.es + kPlaneSlack));
+    RC_TRY(h->ctx.ensure(Mc * m.w_ctx * m.es + kPlaneSlack));
+    RC_TRY(h->u0.ensure(Mc * m.w_u0 * m.es + kPlaneSlack));
+    RC_TRY(h->u1.ensure(Mc * m.w_u1 * m.es + kPlaneSlack));
     {
         const void* s_before = h->s.p; const size_t s_bytes = h->s.bytes;
         RC_TRY(h->s.ensure(R * m.Tp * m.es));
@@ -620,13 +672,14 @@ static int ensure_workspace(vitdet_handle* h, int B, int mode) {
         if (m.Tp != h->T && (h->s.p != s_before || h->s.bytes != s_bytes || h->s_layout_mode != mode)) { CU_TRY(cudaMemset(h->s.p, 0, h->s.bytes)); CU_TRY(cudaDeviceSynchronize()); }
         h->s_layout_mode = mode;
     }
-    RC_TRY(h->h0.ensure(R * m.w_h0 * m.es));
-    RC_TRY(h->h1.ensure(R * m.w_h1 * m.es));
+    RC_TRY(h->h0.ensure(R * m.w_h0 * m.es + kPlaneSlack));
+    RC_TRY(h->h1.ensure(R * m.w_h1 * m.es + kPlaneSlack));
     const void* after[10] = {h->x.p, h->patch.p, h->y.p, h->qkv.p, h->ctx.p, h->u0.p, h->u1.p, h->s.p, h->h0.p, h->h1.p};
     for (int i = 0; i < 10; ++i) {
         if (before[i] != after[i]) {     // a buffer moved: every cached TMA descriptor is stale
             h->enc_plans.clear();
             h->head_plans.clear();
+            h->plans32.clear();
             break;
         }
     }
@@ -796,6 +849,170 @@ struct ForwardOpts {
     int in_u8 = 0;                    // images are uint8 pixels; the patch kernel normalises them (x / 127.5 - 1)
 };
 
+// ------------------------------------------------------------------------------------------------
+// fp32-accumulate mode on the tensor cores (north_star: <= 1e-3 against the float32 reference).
+// Every float32 activation that feeds a Dense layer travels as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)) and
+// every Dense is three tcgen05 passes (hi*hi + hi*lo + lo*hi, float32 accumulation in TMEM) through the same two GEMM
+// kernels as the bf16 mode, with exact expf-based activations in the epilogue.  The residual stream, LayerNorm, the
+// softmax of the attention core (attn_f32_kernel) and the head's slot projection / last Dense stay in IEEE float32.
+// Buffers are the fp32 mode's (4 bytes per element): the hi plane in the first half, the lo plane in the second.
+// ------------------------------------------------------------------------------------------------
+struct Planes { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+static Planes planes_of(const DevBuf& b) {
+    return Planes{b.as<__nv_bfloat16>(), reinterpret_cast<__nv_bfloat16*>(b.as<char>() + (b.bytes / 2 & ~static_cast<size_t>(255)))};
+}
+
+static int forward_fp32_tc(vitdet_handle* h, const void* images, int B, float* logits, const vitdet_decode_params* dpar,
+                           const vitdet_detections* det, cudaStream_t st, const ForwardOpts& opts) {
+    const vitdet_config& c = h->cfg;
+    const int mode = VITDET_MODE_FP32;
+    RC_TRY(ensure_workspace(h, B, mode));
+    const Dims m = dims_for(h, mode);
+    const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
+    const size_t tap_stride = static_cast<size_t>(B) * T * m.D4;
+    if (h->taps_on) { RC_TRY(h->taps.ensure(static_cast<size_t>(L + 1) * tap_stride * 4)); h->taps_B = B; }
+    {
+        const size_t bcmax = static_cast<size_t>(B < h->chunk ? B : h->chunk);
+        size_t need = bcmax * T * round_up(h->PK, 4) * 4;
+        const size_t need_s = static_cast<size_t>(B) * h->S * round_up(T, 8) * 4 + 1024;
+        if (need_s > need) need = need_s;
+        const void* before = h->tmp32.p;
+        RC_TRY(h->tmp32.ensure(need));
+        if (h->tmp32.p != before) h->plans32.clear();
+    }
+    std::vector<TcGemmPlan>& cache = h->plans32[(static_cast<long long>(B) << 20) | h->chunk];
+    const bool build = cache.empty();
+    size_t pi = 0;
+    // one Dense: A planes [M, lda] x W planes -> float32 `out` (+ residual / position) or planes `po`
+    auto dense = [&](int cat, Planes A, int lda, const DenseW& w, int M, float* out, int ldc, const Planes* po, int act,
+                     const float* resid, const float* pos) -> int {
+        if (build) {
+            GemmDesc g;
+            g.A = A.hi; g.A_lo = A.lo; g.lda = lda;
+            g.W = w.w16.p; g.W_lo = w.w16_lo(); g.ldw = w.ld16;
+            g.M = M; g.N = w.N; g.K = w.K;
+            g.bias = w.bias.as<float>();
+            g.pos = pos; g.pos_period = T;
+            g.resid = resid; g.ldr = resid ? ldc : 0;
+            g.split = 1; g.precise = 1; g.act = act;
+            if (po) { g.out = po->hi; g.out_lo = po->lo; g.out_split = 1; g.out_f32 = 0; g.ldc = round_up(w.N, 8); }
+            else { g.out = out; g.out_f32 = 1; g.ldc = ldc; }
+            TcGemmPlan plan;
+            int rc = make_tc_plan(&plan, g, h->num_sms, h->opt.gemm_pair);
+            if (rc) return fail(VITDET_E_INVALID, "fp32 tensor-core plan (M=%d N=%d K=%d) failed: %d", g.M, g.N, g.K, rc);
+            cache.push_back(plan);
+        }
+        TcGemmPlan plan = cache[pi++];
+        if (!po) { plan.desc.out = out; plan.desc.resid = resid; }
+        ProfScope ps(h, cat, st);
+        cudaError_t e = plan.pair ? tc2_gemm_launch(plan, st) : tc_gemm_launch(plan, st);
+        if (e != cudaSuccess) return fail(VITDET_E_CUDA, "fp32 tensor-core GEMM launch failed: %s", cudaGetErrorString(e));
+        return 0;
+    };
+    auto split = [&](const float* src, long long rows, int cols, int lds, Planes dst, int ldd) -> int {
+        ++h->launches;
+        split_rows_kernel<<<blocks_for(rows * (ldd >> 3)), 256, 0, st>>>(src, rows, cols, lds, dst.hi, dst.lo, ldd);
+        CU_TRY(cudaGetLastError());
+        return 0;
+    };
+    const Planes p_patch = planes_of(h->patch), p_y = planes_of(h->y), p_u0 = planes_of(h->u0), p_u1 = planes_of(h->u1),
+                 p_qkv = planes_of(h->qkv), p_ctx = planes_of(h->ctx), p_s = planes_of(h->tmp32);
+
+    for (int c0 = 0, bc = 0, ci = 0; c0 < B; c0 += bc, ++ci) {
+        bc = (B - c0) < h->chunk ? (B - c0) : h->chunk;
+        (void)ci;      // no small lead chunks here: the plan cache is keyed by (batch, chunk) only
+        if (opts.ready) CU_TRY(cudaStreamWaitEvent(st, opts.ready[(c0 + bc + opts.ready_gran - 1) / opts.ready_gran - 1], 0));
+        const int Mc = bc * T;
+        float* x = h->x.as<float>() + static_cast<size_t>(c0) * T * m.D4;
+        const char* img = static_cast<const char*>(images) + static_cast<size_t>(c0) * c.image_h * c.image_w * 3 * (opts.in_u8 ? 1 : 4);
+        const int P4 = round_up(h->PK, 4);
+        float* tmp_big = h->tmp32.as<float>();          // [Mc, P4] float32 patches before the split
+        { ProfScope ps(h, PC_PATCHIFY, st);
+        CU_TRY(patchify_launch(img, opts.in_u8, bc, c.image_h, c.image_w, c.patch_size, tmp_big, P4, h->RP, 1, st)); }
+        RC_TRY(split(tmp_big, Mc, h->PK, P4, p_patch, m.Pld));
+        RC_TRY(dense(PC_PROJ, p_patch, m.Pld, h->proj, Mc, x, m.D4, nullptr, ACT_NONE, nullptr, h->pos.as<float>()));
+        if (h->taps_on) CU_TRY(cudaMemcpyAsync(h->taps.as<float>() + static_cast<size_t>(c0) * T * m.D4, x, static_cast<size_t>(Mc) * m.D4 * 4, cudaMemcpyDeviceToDevice, st));
+        float* tmp_ln = h->tmp32.as<float>();           // [Mc, D4] LayerNorm output before the split
+        for (int i = 0; i < L; ++i) {
+            BlockW& b = h->blocks[i];
+            { ProfScope ps(h, PC_LN, st);
+            CU_TRY(layernorm_launch(x, m.D4, b.ln1_g.as<float>(), b.ln1_b.as<float>(), Mc, h->D, c.ln_epsilon, tmp_ln, m.D4, 1, st)); }
+            RC_TRY(split(tmp_ln, Mc, h->D, m.D4, p_y, m.D8));
+            // q | k | v and the context rows stay in the split form end to end: QKV GEMM -> planes -> attention -> planes
+            RC_TRY(dense(PC_QKV, p_y, m.D8, b.qkv, Mc, nullptr, 0, &p_qkv, ACT_NONE, nullptr, nullptr));
+            {
+                AttnDesc ad;
+                ad.qkv = p_qkv.hi; ad.ldq = m.w_qkv; ad.ctx = p_ctx.hi; ad.ldo = m.w_ctx;
+                ad.B = bc; ad.T = T; ad.H = h->H; ad.d = h->d; ad.hp = h->hp;
+                ad.scale = 1.f / sqrtf(static_cast<float>(h->d));
+                AttnPlan ap;
+                CUtensorMap tm_lo;
+                int rc = attn_bf16_make_plan(&ap, ad);
+                if (!rc) rc = make_tmap_bf16_2d(&tm_lo, p_qkv.lo, bc * T, 3 * h->H * h->hp, m.w_qkv, 64);
+                if (rc) return fail(VITDET_E_INVALID, "fp32 tensor-core attention plan failed: %d", rc);
+                ProfScope ps(h, PC_ATTN, st);
+                CU_TRY(attn_tcs_launch(ap, tm_lo, p_ctx.lo, st));
+            }
+            RC_TRY(dense(PC_OUT, p_ctx, m.w_ctx, b.out, Mc, x, m.D4, nullptr, ACT_NONE, x, nullptr));
+            { ProfScope ps(h, PC_LN, st);
+            CU_TRY(layernorm_launch(x, m.D4, b.ln2_g.as<float>(), b.ln2_b.as<float>(), Mc, h->D, c.ln_epsilon, tmp_ln, m.D4, 1, st)); }
+            RC_TRY(split(tmp_ln, Mc, h->D, m.D4, p_y, m.D8));
+            Planes a = p_y; int lda = m.D8;
+            for (int j = 0; j < q; ++j) {
+                const bool last = j == q - 1;
+                if (last) {
+                    RC_TRY(dense(PC_MLP0 + j, a, lda, b.mlp[j], Mc, x, m.D4, nullptr, h->act, x, nullptr));
+                } else {
+                    const Planes o = (j & 1) ? p_u1 : p_u0;
+                    RC_TRY(dense(PC_MLP0 + j, a, lda, b.mlp[j], Mc, nullptr, 0, &o, h->act, nullptr, nullptr));
+                    a = o; lda = round_up(b.mlp[j].N, 8);
+                }
+            }
+            if (h->taps_on) CU_TRY(cudaMemcpyAsync(h->taps.as<float>() + (i + 1) * tap_stride + static_cast<size_t>(c0) * T * m.D4, x, static_cast<size_t>(Mc) * m.D4 * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+
+    // mlp_head over the whole batch (det.py:454-493)
+    const int R = B * h->S;
+    { ProfScope ps(h, PC_HEAD_SLOTS, st);
+    CU_TRY(head_slots_launch(h->x.as<float>(), m.D4, h->head_slot_w.as<float>(), h->head_slot_b.as<float>(), B * T, h->D, h->S, T, m.Tp,
+                             h->s.p, 1, st)); }
+    const int T8 = round_up(T, 8);
+    RC_TRY(split(h->s.as<float>(), R, T, m.Tp, p_s, T8));
+    Planes a = p_s; int lda = T8;
+    const float* last_out = nullptr; int last_ld = 0;
+    for (size_t i = 0; i < h->head.size(); ++i) {
+        const bool last = i + 1 == h->head.size();
+        DevBuf& ob = (i & 1) ? h->h1 : h->h0;
+        if (last) {
+            last_ld = round_up(h->head[i].N, 4);
+            RC_TRY(dense(PC_HEAD_GEMM, a, lda, h->head[i], R, ob.as<float>(), last_ld, nullptr, h->act, nullptr, nullptr));
+            last_out = ob.as<float>();
+        } else {
+            const Planes o = planes_of(ob);
+            RC_TRY(dense(PC_HEAD_GEMM, a, lda, h->head[i], R, nullptr, 0, &o, h->act, nullptr, nullptr));
+            a = o; lda = round_up(h->head[i].N, 8);
+        }
+    }
+    DecodeParams dp;
+    DecodeOut dout;
+    dout.logits = logits;
+    if (dpar) {
+        dp.obj_thr = dpar->objectness_threshold; dp.cls_thr = dpar->classification_threshold;
+        dp.strict = dpar->strict; dp.img_h = dpar->image_h; dp.img_w = dpar->image_w; dp.classes = dpar->classes;
+        dp.apply_transform = 1;
+        dp.corner_scale = dpar->corner_scale > 0.f ? dpar->corner_scale : 1.f;
+    }
+    if (det) {
+        dout.decoded = det->decoded; dout.class_id = det->class_id; dout.class_conf = det->class_conf;
+        dout.keep = det->keep; dout.corners = det->corners; dout.packed = det->packed;
+    }
+    h->head_last = last_out; h->head_last_ld = last_ld; h->head_last_f32 = 1;
+    ProfScope ps(h, PC_HEAD_TAIL, st);
+    CU_TRY(head_tail_launch(last_out, last_ld, 1, h->tail_w.as<float>(), h->tail_b.as<float>(), R, h->tail_U, dp, dout, st));
+    return 0;
+}
+
 static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, float* logits,
                         const vitdet_decode_params* dpar, const vitdet_detections* det, cudaStream_t st,
                         const ForwardOpts& opts = ForwardOpts()) {
@@ -811,6 +1028,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
         if (!s.set) return fail(VITDET_E_UNSET, "forward: weight '%s' has not been set", s.name.c_str());
     const vitdet_config& c = h->cfg;
     const bool bf = mode == VITDET_MODE_BF16;
+    if (!bf && h->opt.fp32_tc) return forward_fp32_tc(h, images, B, logits, dpar, det, st, opts);
     RC_TRY(ensure_workspace(h, B, mode));
     const Dims m = dims_for(h, mode);
     const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
@@ -1046,7 +1264,7 @@ int vitdet_set_weight(vitdet_handle* h, const char* name_in, const float* data, 
     switch (s.kind) {
         case WeightSlot::DENSE_KERNEL:
             pack_dense_kernel<<<blocks_for(s.count), 256>>>(src, s.K, s.N, s.gn, s.pn, s.row_off, s.gk, s.pk,
-                                                            s.dense->w16.as<__nv_bfloat16>(), s.dense->ld16,
+                                                            s.dense->w16.as<__nv_bfloat16>(), s.dense->ld16, s.dense->lo_off(),
                                                             s.dense->w32.as<float>(), s.dense->ld32);
             break;
         case WeightSlot::DENSE_BIAS:
@@ -1054,7 +1272,7 @@ int vitdet_set_weight(vitdet_handle* h, const char* name_in, const float* data, 
             break;
         case WeightSlot::VEC:
             if (s.vec_transpose)   // keep as f32 [N, K]
-                pack_dense_kernel<<<blocks_for(s.count), 256>>>(src, s.K, s.N, s.N, s.N, 0, s.K, s.K, nullptr, 0, s.vec_dst, s.K);
+                pack_dense_kernel<<<blocks_for(s.count), 256>>>(src, s.K, s.N, s.N, s.N, 0, s.K, s.K, nullptr, 0, 0, s.vec_dst, s.K);
             else
                 CU_TRY(cudaMemcpy(s.vec_dst, src, static_cast<size_t>(s.count) * 4, cudaMemcpyDeviceToDevice));
             break;
@@ -1113,10 +1331,12 @@ int vitdet_set_option(vitdet_handle* h, const char* key, int value) {
     if (k == "fuse_ln") h->opt.fuse_ln = value != 0;
     else if (k == "fuse_tail") h->opt.fuse_tail = value != 0;
     else if (k == "gemm_pair") { if (value < 0 || value > 2) return fail(VITDET_E_INVALID, "set_option(gemm_pair): 0, 1 or 2"); h->opt.gemm_pair = value; }
-    else if (k == "attention") { if (value != 1 && value != 2 && value != 4 && value != 8 && value != 40 && value != 80) return fail(VITDET_E_INVALID, "set_option(attention): 1, 2, 4, 8, 40 or 80"); h->opt.attention = value; }
+    else if (k == "fp32_tc") h->opt.fp32_tc = value != 0;
+    else if (k == "attention") { if (value != 1 && value != 2 && value != 3 && value != 4 && value != 8 && value != 40 && value != 80) return fail(VITDET_E_INVALID, "set_option(attention): 1, 2, 4, 8, 40 or 80"); h->opt.attention = value; }
     else return fail(VITDET_E_NOT_FOUND, "set_option: unknown option '%s'", key);
     h->enc_plans.clear();
     h->head_plans.clear();
+    h->plans32.clear();
     return 0;
 }
 
@@ -1127,6 +1347,7 @@ int vitdet_get_option(const vitdet_handle* h, const char* key, int* value) {
     else if (k == "fuse_tail") *value = h->opt.fuse_tail;
     else if (k == "gemm_pair") *value = h->opt.gemm_pair;
     else if (k == "attention") *value = h->opt.attention;
+    else if (k == "fp32_tc") *value = h->opt.fp32_tc;
     else return fail(VITDET_E_NOT_FOUND, "get_option: unknown option '%s'", key);
     return 0;
 }
@@ -1453,7 +1674,7 @@ int vitdet_op_dense(const float* A, const float* kernel, const float* bias, cons
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DenseW w;
     RC_TRY(w.alloc(N, K));
-    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16,
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16, w.lo_off(),
                                                                                w.w32.as<float>(), w.ld32);
     if (bias) CU_TRY(cudaMemcpyAsync(w.bias.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, st));
     const int N4 = round_up(N, 4);
@@ -1475,6 +1696,25 @@ int vitdet_op_dense(const float* A, const float* kernel, const float* bias, cons
         GemmDesc g = make_desc(c, VITDET_MODE_BF16);
         rc = make_tc_plan(&plan, g, sms, env_options().gemm_pair);
         if (rc) return fail(VITDET_E_INVALID, "op_dense: tc_gemm_make_plan failed: %d", rc);
+        RC_TRY(launch_tc(plan, o_buf.p, rp, st));
+    } else if (env_options().fp32_tc) {
+        // fp32-accumulate mode on the tensor cores: split (hi, lo) bf16 planes, three passes, exact activation
+        const int K8 = round_up(K, 8);
+        RC_TRY(a_buf.ensure(static_cast<size_t>(M) * K8 * 2 * 2));
+        __nv_bfloat16* a_hi = a_buf.as<__nv_bfloat16>();
+        __nv_bfloat16* a_lo = a_hi + static_cast<size_t>(M) * K8;
+        split_rows_kernel<<<blocks_for(static_cast<long long>(M) * (K8 >> 3)), 256, 0, st>>>(A, M, K, K, a_hi, a_lo, K8);
+        GemmDesc g;
+        g.A = a_hi; g.A_lo = a_lo; g.lda = K8;
+        g.W = w.w16.p; g.W_lo = w.w16_lo(); g.ldw = w.ld16;
+        g.M = M; g.N = N; g.K = K;
+        g.bias = w.bias.as<float>();
+        g.resid = rp; g.ldr = N4;
+        g.out = o_buf.p; g.ldc = N4; g.out_f32 = 1; g.act = act;
+        g.split = 1; g.precise = 1;
+        TcGemmPlan plan;
+        rc = make_tc_plan(&plan, g, sms, env_options().gemm_pair);
+        if (rc) return fail(VITDET_E_INVALID, "op_dense: fp32 tensor-core plan failed: %d", rc);
         RC_TRY(launch_tc(plan, o_buf.p, rp, st));
     } else {
         const int K4 = round_up(K, 4);
@@ -1530,6 +1770,29 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
         { int dev2 = 0, sms2 = 148; CU_TRY(cudaGetDevice(&dev2)); CU_TRY(cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2));
           CU_TRY(attn_launch(env_options().attention, plan, sms2, st)); }
         unpack_ctx_kernel<__nv_bfloat16><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<__nv_bfloat16>(), rows, H, d, hp, out);
+    } else if (env_options().fp32_tc) {
+        // fp32-accumulate mode on the tensor cores: q | k | v as (hi, lo) planes, three-pass products (attention_tcs.cu)
+        const int ld = 3 * H * hp;
+        DevBuf planes, cplanes;
+        RC_TRY(planes.ensure(static_cast<size_t>(rows) * ld * 2 * 2));
+        RC_TRY(cplanes.ensure(static_cast<size_t>(rows) * H * hp * 2 * 2));
+        pack_qkv_kernel<float><<<blocks_for(rows * ld), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<float>());
+        __nv_bfloat16* q_hi = planes.as<__nv_bfloat16>();
+        __nv_bfloat16* q_lo = q_hi + static_cast<size_t>(rows) * ld;
+        __nv_bfloat16* c_hi = cplanes.as<__nv_bfloat16>();
+        __nv_bfloat16* c_lo = c_hi + static_cast<size_t>(rows) * H * hp;
+        split_rows_kernel<<<blocks_for(rows * (ld >> 3)), 256, 0, st>>>(qkv.as<float>(), rows, ld, ld, q_hi, q_lo, ld);
+        ad.qkv = q_hi; ad.ctx = c_hi;
+        AttnPlan plan;
+        CUtensorMap tm_lo;
+        int rc = attn_bf16_make_plan(&plan, ad);
+        if (!rc) rc = make_tmap_bf16_2d(&tm_lo, q_lo, static_cast<int>(rows), ld, ld, 64);
+        if (rc) return fail(VITDET_E_INVALID, "op_attention: fp32 tensor-core plan failed: %d", rc);
+        CU_TRY(attn_tcs_launch(plan, tm_lo, c_lo, st));
+        unpack_ctx_planes_kernel<<<blocks_for(rows * H * d), 256, 0, st>>>(c_hi, c_lo, rows, H, d, hp, out);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(st));
+        return 0;
     } else {
         pack_qkv_kernel<float><<<blocks_for(rows * 3 * H * hp), 256, 0, st>>>(q, k, v, rows, H, d, hp, qkv.as<float>());
         CU_TRY(attn_f32_launch(ad, st));
@@ -1558,7 +1821,7 @@ int vitdet_op_dense_ex(const float* A, const float* kernel, const float* bias, c
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DenseW w;
     RC_TRY(w.alloc(N, K));
-    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16,
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(K) * N), 256, 0, st>>>(kernel, K, N, N, N, 0, K, K, w.w16.as<__nv_bfloat16>(), w.ld16, w.lo_off(),
                                                                                w.w32.as<float>(), w.ld32);
     if (bias) CU_TRY(cudaMemcpyAsync(w.bias.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, st));
     const int N4 = round_up(N, 4), N8 = round_up(N, 8), K8 = round_up(K, 8);
@@ -1609,7 +1872,7 @@ int vitdet_op_mlp_tail(const float* A, const float* W0, const float* b0, const f
     for (int l = 0; l < 3; ++l) {
         RC_TRY(w[l].alloc(N[l], K[l]));
         pack_dense_kernel<<<blocks_for(static_cast<long long>(K[l]) * N[l]), 256, 0, st>>>(Wk[l], K[l], N[l], N[l], N[l], 0, K[l], K[l],
-                                                                                         w[l].w16.as<__nv_bfloat16>(), w[l].ld16, nullptr, 0);
+                                                                                         w[l].w16.as<__nv_bfloat16>(), w[l].ld16, 0, nullptr, 0);
         CU_TRY(cudaMemcpyAsync(w[l].bias.p, bk[l], static_cast<size_t>(N[l]) * 4, cudaMemcpyDeviceToDevice, st));
     }
     const int K8 = round_up(K0, 8), D4 = round_up(N2, 4), D8 = round_up(N2, 8);
@@ -1651,7 +1914,7 @@ int vitdet_op_head_slots(const float* x, const float* kernel, const float* bias,
     RC_TRY(ob.ensure(static_cast<size_t>(R) * Tp * (bf ? 2 : 4)));
     CU_TRY(cudaMemsetAsync(ob.p, 0, ob.bytes, st));
     pad_rows_f32_kernel<<<blocks_for(M * D4), 256, 0, st>>>(x, static_cast<int>(M), D, D, xb.as<float>(), D4);
-    pack_dense_kernel<<<blocks_for(static_cast<long long>(D) * S), 256, 0, st>>>(kernel, D, S, S, S, 0, D, D, nullptr, 0, wt.as<float>(), D);
+    pack_dense_kernel<<<blocks_for(static_cast<long long>(D) * S), 256, 0, st>>>(kernel, D, S, S, S, 0, D, D, nullptr, 0, 0, wt.as<float>(), D);
     CU_TRY(head_slots_launch(xb.as<float>(), D4, wt.as<float>(), bias, static_cast<int>(M), D, S, tokens, Tp, ob.p, bf ? 0 : 1, st));
     if (bf) bf16_rows_to_f32_kernel<<<blocks_for(R * tokens), 256, 0, st>>>(ob.as<__nv_bfloat16>(), static_cast<int>(R), tokens, Tp, out);
     else unpad_rows_f32_kernel<<<blocks_for(R * tokens), 256, 0, st>>>(ob.as<float>(), static_cast<int>(R), tokens, Tp, out);

@@ -57,12 +57,16 @@ struct Tc2GemmArgs {
     void* out;
     int ldc;
     int n_store;   // round_up(N, store vector): columns [N, n_store) are written as zero
+    int split;     // 1: A and W are (hi, lo) bf16 planes; three passes over K (hi*hi, hi*lo, lo*hi)
 };
 
-template <int ACT, bool OUT_F32>
+// OUT: 0 bf16 (TMA store), 1 float32, 2 split bf16 planes (hi, lo); PRECISE: exact activations (fp32-accumulate mode)
+template <int ACT, int OUT, bool PRECISE>
 __global__ void __launch_bounds__(kThreads, 1)   // 96 registers is the most 576 threads can be granted (104 and 112 fail to launch)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const Tc2GemmArgs p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmC_lo, const Tc2GemmArgs p) {
+    constexpr bool OUT_F32 = OUT == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_s;
@@ -73,7 +77,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0u) __trap();          // 128B-swizzled stages need 1024-byte alignment
-    const uint32_t s_store0 = smem_base + kRingBytes; // epilogue store staging, one 2 KB tile per warp
+    // epilogue store staging after the ring: one 2 KB tile per warp, two (hi, lo) in the split-output mode
+    constexpr uint32_t kStoreStride = OUT == 2 ? 2 * kStoreTileBytes : kStoreTileBytes;
+    const uint32_t s_store0 = smem_base + (OUT == 2 ? kRingBytes - kStoreBytes : kRingBytes);
     const uint32_t stage_bytes_b = static_cast<uint32_t>(p.block_n / 2) * (kBK * 2);      // this CTA's half of the W tile
     const uint32_t cta_rank = cluster_ctarank();
     const bool leader = cta_rank == 0;
@@ -100,6 +106,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (!OUT_F32) tma_prefetch_desc(&tmC);
+        if (PRECISE && p.split) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+        if (OUT == 2) tma_prefetch_desc(&tmC_lo);
     }
     if (warp == kMmaWarp) {
         tmem_alloc_2sm(smem_u32(&tmem_base_s), kTmemCols);
@@ -123,11 +131,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int m0 = (tile / p.n_tiles) * (2 * kBM) + static_cast<int>(cta_rank) * kBM;
                 const int n0 = (tile % p.n_tiles) * p.block_n + static_cast<int>(cta_rank) * (p.block_n / 2);
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                    if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
-                    tma_load_2d_2sm(sA0 + stage * kStageBytesA, &tmA, bar_full_leader + 8 * stage, kb * kBK, m0);
-                    tma_load_2d_2sm(sB0 + stage * stage_bytes_b, &tmB, bar_full_leader + 8 * stage, kb * kBK, n0);
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    // split mode: the k-block is visited three times, with (A, W) = (hi, hi), (hi, lo), (lo, hi)
+                    for (int t = 0; t < ((PRECISE && p.split) ? 3 : 1); ++t) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                        if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+                        tma_load_2d_2sm(sA0 + stage * kStageBytesA, t == 2 ? &tmA_lo : &tmA, bar_full_leader + 8 * stage, kb * kBK, m0);
+                        tma_load_2d_2sm(sB0 + stage * stage_bytes_b, t == 1 ? &tmB_lo : &tmB, bar_full_leader + 8 * stage, kb * kBK, n0);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
@@ -149,21 +160,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+                const int passes = (PRECISE && p.split) ? 3 : 1;      // split planes only exist in the fp32-accumulate mode
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
                     const int ksteps = (kb == p.num_kb - 1) ? last_steps : kBK / kUK;
-                    if (elect_one()) {
-                        const uint64_t da = da0 + static_cast<uint64_t>(stage * a_step), db = db0 + static_cast<uint64_t>(stage * b_step);
-                        umma_bf16_ss_2sm(d_tmem, da, db, idesc, kb != 0);
-                        if (ksteps > 1) umma_bf16_ss_2sm(d_tmem, da + 2u, db + 2u, idesc, 1u);
-                        if (ksteps > 2) umma_bf16_ss_2sm(d_tmem, da + 4u, db + 4u, idesc, 1u);
-                        if (ksteps > 3) umma_bf16_ss_2sm(d_tmem, da + 6u, db + 6u, idesc, 1u);
-                        umma_commit_2sm(bar_empty + 8 * stage, 3);          // frees the stage in both CTAs
-                        if (kb == p.num_kb - 1) umma_commit_2sm(bar_tfull + 8 * acc, 3);   // accumulators of both CTAs complete
+                    for (int t = 0; t < passes; ++t) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = da0 + static_cast<uint64_t>(stage * a_step), db = db0 + static_cast<uint64_t>(stage * b_step);
+                            umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | t) != 0);
+                            if (ksteps > 1) umma_bf16_ss_2sm(d_tmem, da + 2u, db + 2u, idesc, 1u);
+                            if (ksteps > 2) umma_bf16_ss_2sm(d_tmem, da + 4u, db + 4u, idesc, 1u);
+                            if (ksteps > 3) umma_bf16_ss_2sm(d_tmem, da + 6u, db + 6u, idesc, 1u);
+                            umma_commit_2sm(bar_empty + 8 * stage, 3);          // frees the stage in both CTAs
+                            if (kb == p.num_kb - 1 && t == passes - 1) umma_commit_2sm(bar_tfull + 8 * acc, 3);   // accumulators of both CTAs complete
+                        }
+                        __syncwarp();
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -203,7 +217,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (full && p.N > 32) {
                         // wide float32 output (embedding_dim > 32): finished values of the lane's row, 16 columns at a
                         // time, through the staging tile to coalesced stores (common.cuh); residual added on that side
-                        const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreTileBytes;
+                        const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreStride;
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             float y16[16];
@@ -211,10 +225,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int g = 0; g < 4; ++g) {
                                 const int c = c0 + 16 * hh + 4 * g;
                                 const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                y16[4 * g + 0] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 0]) + b4.x + pos_v);
-                                y16[4 * g + 1] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 1]) + b4.y + pos_v);
-                                y16[4 * g + 2] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 2]) + b4.z + pos_v);
-                                y16[4 * g + 3] = apply_act<ACT, false>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
+                                y16[4 * g + 0] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 0]) + b4.x + pos_v);
+                                y16[4 * g + 1] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 1]) + b4.y + pos_v);
+                                y16[4 * g + 2] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 2]) + b4.z + pos_v);
+                                y16[4 * g + 3] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
                             }
                             store_f32_half_chunk_coalesced(s_tile, y16, lane, m0 + quad * 32, p.M, reinterpret_cast<float*>(p.out), p.ldc,
                                                            p.resid, p.ldr, n0 + c0 + 16 * hh);
@@ -244,7 +258,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float y = apply_act<ACT, false>(x[j] + pos_v) + r[j];
+                                const float y = apply_act<ACT, PRECISE>(x[j] + pos_v) + r[j];
                                 x[j] = (full || n + j < p.N) ? y : 0.f;
                             }
                             *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
@@ -256,9 +270,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     // which is both what CU_TENSOR_MAP_SWIZZLE_64B expects and bank-conflict free), then
                     // one TMA store writes it with full 64-byte row segments.  Rows >= M and columns past
                     // the tensor width are clipped by the TMA unit.
-                    const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreTileBytes;
+                    const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreStride;
                     uint32_t o[16];
-                    if (full) {
+                    uint32_t olo[OUT == 2 ? 16 : 1];
+                    if (OUT == 2) {
+                        // split output: y in float32 with the exact activation, hi = bf16(y), lo = bf16(y - hi)
+#pragma unroll
+                        for (int g = 0; g < 16; ++g) {
+                            const int n = n0 + c0 + 2 * g;
+                            const float bb0 = (p.bias && n < p.N) ? __ldg(bs + c0 + 2 * g) : 0.f;
+                            const float bb1 = (p.bias && n + 1 < p.N) ? __ldg(bs + c0 + 2 * g + 1) : 0.f;
+                            float y0 = apply_act<ACT, PRECISE>(__uint_as_float(v[2 * g + 0]) + bb0);
+                            float y1 = apply_act<ACT, PRECISE>(__uint_as_float(v[2 * g + 1]) + bb1);
+                            if (n >= p.N) y0 = 0.f;
+                            if (n + 1 >= p.N) y1 = 0.f;
+                            const __nv_bfloat162 hi = __floats2bfloat162_rn(y0, y1);
+                            o[g] = *reinterpret_cast<const uint32_t*>(&hi);
+                            olo[g] = pack_bf16x2(y0 - __low2float(hi), y1 - __high2float(hi));
+                        }
+                    } else if (full) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c0 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -285,11 +315,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint32_t dst = s_tile + static_cast<uint32_t>(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * g]), "r"(o[4 * g + 1]),
                                      "r"(o[4 * g + 2]), "r"(o[4 * g + 3]) : "memory");
+                        if (OUT == 2)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kStoreTileBytes), "r"(olo[(4 * g) % (OUT == 2 ? 16 : 1)]),
+                                         "r"(olo[(4 * g + 1) % (OUT == 2 ? 16 : 1)]), "r"(olo[(4 * g + 2) % (OUT == 2 ? 16 : 1)]),
+                                         "r"(olo[(4 * g + 3) % (OUT == 2 ? 16 : 1)]) : "memory");
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         tma_store_2d(&tmC, s_tile, n0 + c0, m0 + quad * 32);
+                        if (OUT == 2) tma_store_2d(&tmC_lo, s_tile + kStoreTileBytes, n0 + c0, m0 + quad * 32);
                         tma_store_commit();
                     }
                 }
@@ -312,14 +347,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-template <int ACT, bool OUT_F32>
+template <int ACT, int OUT, bool PRECISE>
 cudaError_t launch_variant2(const TcGemmPlan& plan, const Tc2GemmArgs& a, cudaStream_t stream) {
-    auto kern = gemm_tc2_kernel<ACT, OUT_F32>;
+    auto kern = gemm_tc2_kernel<ACT, OUT, PRECISE>;
     {
         cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(kern), kMaxDynSmem);
         if (e != cudaSuccess) return e;
     }
-    return launch_kernel(kern, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, 2, plan.tmA, plan.tmB, plan.tmC, a);
+    return launch_kernel(kern, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, 2, plan.tmA, plan.tmB, plan.tmC, plan.tmA_lo,
+                         plan.tmB_lo, plan.tmC_lo, a);
+}
+
+template <int ACT>
+cudaError_t launch_act2(const TcGemmPlan& plan, const Tc2GemmArgs& a, cudaStream_t stream) {
+    const GemmDesc& d = plan.desc;
+    if (d.out_f32) return d.precise ? launch_variant2<ACT, 1, true>(plan, a, stream) : launch_variant2<ACT, 1, false>(plan, a, stream);
+    if (d.out_split) return launch_variant2<ACT, 2, true>(plan, a, stream);
+    return launch_variant2<ACT, 0, false>(plan, a, stream);
 }
 
 }  // namespace
@@ -336,13 +380,17 @@ int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     if (d.resid && (!d.out_f32 || (d.ldr % 4) || d.ldr < (d.N + 3) / 4 * 4)) return -6;
     if (d.pos && !d.out_f32) return -8;
     if (d.ln_out) return -9;       // the fused LayerNorm exists in the single-CTA kernel only (N <= 32 layers)
+    if (d.split && !d.precise) return -12;      // split planes belong to the fp32-accumulate (precise) instantiations
+    if (d.split && (!d.A_lo || !d.W_lo || (reinterpret_cast<uintptr_t>(d.A_lo) & 15) || (reinterpret_cast<uintptr_t>(d.W_lo) & 15))) return -10;
+    if (d.out_split && (d.out_f32 || !d.out_lo || (reinterpret_cast<uintptr_t>(d.out_lo) & 15))) return -11;
     int bn = d.block_n > 0 ? d.block_n : choose_block_n(d.N);
     if (bn % 32 || bn < 32 || bn > kMaxBN) return -7;
 
     plan->desc = d;
     plan->block_n = bn;
     const int stage = kStageBytesA + (bn / 2) * kBK * 2;
-    int stages = kRingBytes / stage;
+    const int ring = d.out_split ? kRingBytes - kStoreBytes : kRingBytes;       // split output: two staging tiles per epilogue warp
+    int stages = ring / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     plan->num_stages = stages;
     plan->smem_bytes = kMaxDynSmem;
@@ -358,6 +406,15 @@ int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     if (r) return r;
     if (!d.out_f32) r = make_tmap_bf16_2d_ex(&plan->tmC, d.out, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
     else plan->tmC = plan->tmA;
+    if (r) return r;
+    plan->tmA_lo = plan->tmA; plan->tmB_lo = plan->tmB; plan->tmC_lo = plan->tmC;      // placeholders when unused
+    if (d.split) {
+        r = make_tmap_bf16_2d(&plan->tmA_lo, d.A_lo, d.M, d.K, d.lda, kBM);
+        if (r) return r;
+        r = make_tmap_bf16_2d(&plan->tmB_lo, d.W_lo, d.N, d.K, d.ldw, bn / 2);
+        if (r) return r;
+    }
+    if (d.out_split) r = make_tmap_bf16_2d_ex(&plan->tmC_lo, d.out_lo, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
     return r;
 }
 
@@ -378,18 +435,11 @@ cudaError_t tc2_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
     a.out = d.out;
     a.ldc = d.ldc;
     a.n_store = d.out_f32 ? (d.N + 3) / 4 * 4 : (d.N + 7) / 8 * 8;
-    if (d.out_f32) {
-        switch (d.act) {
-            case ACT_NONE: return launch_variant2<ACT_NONE, true>(plan, a, stream);
-            case ACT_MISH: return launch_variant2<ACT_MISH, true>(plan, a, stream);
-            case ACT_GELU: return launch_variant2<ACT_GELU, true>(plan, a, stream);
-        }
-    } else {
-        switch (d.act) {
-            case ACT_NONE: return launch_variant2<ACT_NONE, false>(plan, a, stream);
-            case ACT_MISH: return launch_variant2<ACT_MISH, false>(plan, a, stream);
-            case ACT_GELU: return launch_variant2<ACT_GELU, false>(plan, a, stream);
-        }
+    a.split = d.split;
+    switch (d.act) {
+        case ACT_NONE: return launch_act2<ACT_NONE>(plan, a, stream);
+        case ACT_MISH: return launch_act2<ACT_MISH>(plan, a, stream);
+        case ACT_GELU: return launch_act2<ACT_GELU>(plan, a, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -38,11 +38,23 @@ struct GemmDesc {
     float ln_eps = 1e-3f;
     void* ln_out = nullptr;    // bf16 [M, ln_ld]
     int ln_ld = 0;
+    // fp32-accumulate mode on the tensor cores: every float32 value travels as TWO bf16 planes, hi = bf16(x) and
+    // lo = bf16(x - hi) (|x - hi - lo| <= 2^-18 |x|), and the product is A_hi W_hi + A_hi W_lo + A_lo W_hi — three passes
+    // over K through the same pipeline (the lo*lo term, 2^-18 of the result, is dropped).  split = 1: A_lo / W_lo are the
+    // lo planes (same shapes and pitches as A / W).  out_split = 1 (bf16 output only): the result is stored as planes too,
+    // out = hi, out_lo = lo.  precise = 1: exact expf / tanhf based activations instead of the ex2/rcp.approx forms.
+    int split = 0;
+    const void* A_lo = nullptr;
+    const void* W_lo = nullptr;
+    int out_split = 0;
+    void* out_lo = nullptr;
+    int precise = 0;
 };
 
 struct TcGemmPlan {
     CUtensorMap tmA, tmB;
     CUtensorMap tmC;           // bf16 outputs only: 32 x 32 boxes, 64B swizzle (TMA store from the epilogue)
+    CUtensorMap tmA_lo, tmB_lo, tmC_lo;      // the lo planes of the split (fp32-accumulate) mode
     GemmDesc desc;
     int block_n = 0;
     int num_stages = 0;
@@ -115,9 +127,13 @@ cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tc
 cudaError_t attn_tc8_launch(const AttnPlan& plan, cudaStream_t stream);    // tcgen05 kernel, score rows split over warp pairs (attention_tc8.cu)
 cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);   // persistent form of attention_tc.cu (attention_tcp.cu)
 cudaError_t attn_sw_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent, software-pipelined softmax warps (attention_sw.cu)
+cudaError_t attn_tc3_launch(const AttnPlan& plan, cudaStream_t stream);    // 64-key tiles, three CTAs per SM (attention_tc3.cu)
 cudaError_t attn_pp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent ping-pong: two work streams per CTA take turns on the SFU (attention_pp.cu)
 cudaError_t attn_tc8p_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);  // persistent + split score rows (attention_tc8p.cu)
 cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
+// fp32-accumulate mode on the tensor cores (attention_tcs.cu): plan.desc.qkv / ctx are the hi planes, tm_lo the tensor map
+// of the lo plane of qkv (same shape and pitch), ctx_lo the lo plane of the context rows.
+cudaError_t attn_tcs_launch(const AttnPlan& plan, const CUtensorMap& tm_lo, void* ctx_lo, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Memory-bound row kernels
