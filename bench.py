@@ -317,6 +317,7 @@ class Bench:
         return ms_total, launches, prof, clocks
 
     def time_host(self, model, x_np, img_size, steps, pipelined: bool, bytes_per_elem: int, cfg, B):
+        pixels = bytes_per_elem == 1          # uint8 pixels: normalised inside the patch kernel
         """The reference-facing call with HOST buffers: H2D copy of every step's images, forward + decode, D2H read of
         the records, all inside the timed region.  pipelined: two submissions in flight (submit / collect), so the copy of
         step i+1 overlaps the compute of step i; otherwise one synchronous detect() per step."""
@@ -330,15 +331,15 @@ class Bench:
 
         def run(n):
             if pipelined:
-                t = model.submit(x_np, image_size=img_size, packed=world > 1)
+                t = model.submit(x_np, image_size=img_size, packed=world > 1, normalize_uint8=pixels)
                 for _ in range(n - 1):
-                    t2 = model.submit(x_np, image_size=img_size, packed=world > 1)
+                    t2 = model.submit(x_np, image_size=img_size, packed=world > 1, normalize_uint8=pixels)
                     finish(model.collect(t))
                     t = t2
                 finish(model.collect(t))
             else:
                 for _ in range(n):
-                    finish(model.detect(x_np, image_size=img_size, packed=world > 1))
+                    finish(model.detect(x_np, image_size=img_size, packed=world > 1, normalize_uint8=pixels))
 
         run(2)
         self.barrier()
@@ -424,9 +425,12 @@ def run_ours(args):
     step = b.step_fn(model, x_dev, img_size)
     names = model.profile_categories()
     dominant = "gemm_mlp_2" if "gemm_mlp_2" in names else names[-1]
-    ms_total, launches, prof, clocks = b.time_device(model, step, args.steps, args.warmup, [dominant, "attention"])
+    # the timed region: only the dominant GEMM's launches carry engine events (16 per step), as little perturbation as
+    # the roofline needs; the attention kernel is timed the same way in a second pass right after, outside the headline
+    ms_total, launches, prof, clocks = b.time_device(model, step, args.steps, args.warmup, [dominant])
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+    ms_total_a, _, prof_a, clocks_a = b.time_device(model, step, args.steps, 1, ["attention"]) if args.mode == "bf16" else (None, None, {}, None)
     roofline = gemm_roofline(cfg, B, args.steps, prof, dominant, ms_total, pk) if args.mode == "bf16" else None
     if roofline is not None:
         tpath = os.path.join(ROOT, "profiles", "gemm_mlp_2_traffic.json")
@@ -439,7 +443,9 @@ def run_ours(args):
                 roofline["traffic"] = tj.get("traffic_bytes_per_launch")
             else:
                 roofline["traffic_note"] = "profiles/gemm_mlp_2_traffic.json was captured on another source tree / launch size: not quoted"
-    roof_attn = attention_roofline(cfg, B, args.steps, prof, ms_total, pk, clocks) if args.mode == "bf16" else None
+    roof_attn = attention_roofline(cfg, B, args.steps, prof_a, ms_total_a, pk, clocks_a) if args.mode == "bf16" else None
+    if roof_attn is not None:
+        roof_attn["timing"] = "second pass of the same K steps with engine events around the attention launches only"
 
     # ---- multi-GPU parity: the gathered records of the first images of every rank == rank 0's own run on those images ----
     parity = None

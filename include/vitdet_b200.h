@@ -125,8 +125,8 @@ int64_t vitdet_launch_count(vitdet_handle* h, int reset);
  *   "gemm_pair"  1 (default): CTA-pair GEMM for K >= 512 layers; 0: never; 2: wherever it is legal
  *   "fp32_tc"    1 (default): the fp32 mode's Dense layers run on the tensor cores as three-pass split-bf16 products with
  *                float32 accumulation; 0: IEEE float32 FMA kernels on the CUDA cores (the strict reference form)
- *   "attention"  40 (default): persistent kernel (attention_tcp.cu); 4: one CTA per 128-query work item (attention_tc.cu);
- *                8: score rows split over warp pairs (attention_tc8.cu) */
+ *   "attention"  4 (default and, in a product build, the only value): attention_tc.cu; builds made with
+ *                VITDET_BUILD_EXPERIMENTS=1 also hold the measured-and-dropped kernels of experiments/attention/ */
 int vitdet_set_option(vitdet_handle* h, const char* key, int value);
 int vitdet_get_option(const vitdet_handle* h, const char* key, int* value);
 

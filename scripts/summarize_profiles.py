@@ -94,6 +94,10 @@ def traffic(tag):
     out = {"kernel": row[hdr.index("Kernel Name")][:80], "dram_bytes_read": val("dram__bytes_read.sum"),
            "dram_bytes_write": val("dram__bytes_write.sum"), "source": f"profiles/{tag}_ncu_gemm.md (ncu --set full, B = 64)"}
     out["traffic_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
+    # stamp: bench.py quotes the figure only for the source tree and launch size it was captured on
+    hp = os.path.join(OUT, "csrc_hash.txt")
+    out["csrc_hash"] = open(hp).read().strip() if os.path.exists(hp) else None
+    out["rows_per_launch"] = 64 * 1296
     with open(os.path.join(PROF, "gemm_mlp_2_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
 
@@ -103,9 +107,9 @@ if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
     traffic(tag)
-    for rep in sorted(x[:-8] for x in os.listdir(OUT) if x.endswith(".ncu-rep")):
+    for rep in sorted(x[:-8] for x in os.listdir(OUT) if x.endswith(".ncu-rep") and x.startswith("prof_")):
         full(tag, rep)
-    for name in ("bench_n1.json", "bench_metric.json", "pytest_gpu.log"):
+    for name in ("bench_n1.json", "bench_metric.json", "pytest_gpu.log", "bench_reference_n1.json", "smoke.log", "bench_fp32.json"):
         if os.path.exists(os.path.join(OUT, name)):
             shutil.copy(os.path.join(OUT, name), os.path.join(PROF, f"{tag}_{name}"))
     print(sorted(os.listdir(PROF)))

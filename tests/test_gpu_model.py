@@ -331,8 +331,9 @@ def test_full_size_batch_properties():
 
 
 def test_uint8_pixels_are_normalised_on_the_device_bit_exactly():
-    """uint8 input ("next" row N4 fused into the patch kernel): x / 127.5 - 1 (utilities.py:446-447) happens inside
-    patchify, so predict(uint8) must equal predict(normalised float32) bit for bit, on the host and the device path."""
+    """uint8 input ("next" row N4 fused into the patch kernel): with normalize_uint8=True x / 127.5 - 1 (utilities.py:446-447)
+    happens inside patchify, so the result must equal predict(normalised float32) bit for bit, on the host and the device
+    path; WITHOUT the flag a uint8 array is only cast to float32, as keras Model.predict does."""
     import torch
     cfg = tiny_config()
     rng = np.random.default_rng(7)
@@ -343,9 +344,13 @@ def test_uint8_pixels_are_normalised_on_the_device_bit_exactly():
     for mode in ("fp32", "bf16"):
         model = build_model(cfg, vd.random_weights(cfg, seed=3, spread=True), mode)
         ref = model.predict(f32)
-        assert np.array_equal(model.predict(u8), ref)
-        assert np.array_equal(model(torch.from_numpy(u8).cuda()).cpu().numpy(), ref)
-        a, b = model.detect(u8), model.detect(f32)
+        assert np.array_equal(model.predict(u8, normalize_uint8=True), ref)
+        assert np.array_equal(model(torch.from_numpy(u8).cuda(), normalize_uint8=True).cpu().numpy(), ref)
+        a, b = model.detect(u8, normalize_uint8=True), model.detect(f32)
         assert np.array_equal(a.keep, b.keep) and np.array_equal(a.class_id, b.class_id) and np.array_equal(a.decoded, b.decoded)
-        d = model.detect(torch.from_numpy(u8).cuda())
+        d = model.detect(torch.from_numpy(u8).cuda(), normalize_uint8=True)
         assert np.array_equal(d.decoded.cpu().numpy(), b.decoded) and np.array_equal(d.corners.cpu().numpy(), b.corners)
+        # the Keras semantics: a plain dtype cast
+        cast = model.predict(u8.astype(np.float32))
+        assert np.array_equal(model.predict(u8), cast)
+        assert np.array_equal(model(torch.from_numpy(u8).cuda()).cpu().numpy(), cast)

@@ -159,3 +159,51 @@ def test_resize_with_pad_geometry_and_preprocess():
     o3 = oracle.preprocess_image(flat, (64, 64))
     inside = o3[(o3 != -1).any(axis=-1)]
     assert np.allclose(inside, 200 / 127.5 - 1, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the second restatement and the bf16-faithful mode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_kw", [dict(), dict(use_mish=False, input_shape=(136, 68, 3), encoder_num_heads=3, encoder_key_dim=24,
+                                                 mlp_head_dense_mish_block_repeats=2),
+                                    dict(input_shape=(64, 64, 3), patch_size=16, embedding_dim=64, encoder_num_heads=4, encoder_key_dim=64),
+                                    dict(input_shape=(70, 100, 3))])
+def test_second_restatement_agrees_with_the_first(cfg_kw):
+    """oracle/vitdet_oracle_torchnn.py is written on other primitives (F.unfold, nn.MultiheadAttention with its packed
+    in-projection, nn.LayerNorm, F.mish / F.gelu, nn.Linear): a misreading of SAME padding, of the patch vector order, of the
+    MHA kernel layouts, of the q scaling or of the head's flat Reshape in ONE of the two would show here."""
+    import vitdet_oracle_torchnn as second
+    from _util import tiny_config, images
+    import vision_transformer_detector_b200 as vd
+    cfg = tiny_config(**cfg_kw)
+    w = vd.random_weights(cfg, seed=11, spread=True)
+    x = images(cfg, 3)
+    a = oracle.forward(w, cfg, x, np.float64)
+    b = second.forward(w, cfg, x)
+    assert np.abs(a - b).max() <= 1e-9 * np.abs(a).max()
+
+
+def test_bf16_round_is_round_to_nearest_even():
+    import torch
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(size=4000) * 3.3, [1.00390625, 1.01171875, -1.00390625, 0.0, 3.0e38, 1e-40, -2.5e-7]]).astype(np.float32)
+    assert np.array_equal(oracle.bf16_round(x), torch.from_numpy(x).to(torch.bfloat16).to(torch.float64).numpy())
+    assert oracle.bf16_round(np.array([[1.0, 2.0]])).shape == (1, 2)
+
+
+def test_bf16_faithful_mode_is_consistent():
+    """forward_bf16 = forward with the product's operand roundings: equal to the float64 forward when nothing needs
+    rounding is impossible to arrange for a whole model, so check the two ends: it stays within the bf16 tolerance of the
+    float64 result, and its first tap is exactly bf16(patches) @ bf16(W) + b + pos."""
+    from _util import tiny_config, images, rel_err
+    import vision_transformer_detector_b200 as vd
+    cfg = tiny_config()
+    w = vd.random_weights(cfg, seed=11, spread=True)
+    x = images(cfg, 2)
+    ref = oracle.forward(w, cfg, x, np.float64)
+    got, inter = oracle.forward_bf16(w, cfg, x, return_intermediates=True)
+    assert 1e-4 < rel_err(got, ref) < 2e-2
+    R = oracle.bf16_round
+    emb = R(oracle.extract_patches(x, cfg.patch_size)) @ R(w["linear_projection/kernel"]) + w["linear_projection/bias"].astype(np.float64) \
+        + w["position_encoding/position_embedding/embeddings"].astype(np.float64)[None]
+    assert np.array_equal(inter["embedded_patches"], emb)

@@ -16,12 +16,22 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libvitdet_b200.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libvitdet_b200.stamp")
 
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention.cu", "attention_tc.cu", "attention_tc8.cu", "attention_tcp.cu", "attention_tcs.cu", "attention_tc3.cu", "attention_sw.cu", "attention_pp.cu", "attention_tc8p.cu", "mlp_tail.cu", "rowops.cu", "metric.cu", "gather.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention.cu", "attention_tc.cu", "attention_tcs.cu", "mlp_tail.cu", "rowops.cu", "metric.cu", "gather.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
+
+
+# VITDET_BUILD_EXPERIMENTS=1 also compiles the measured-and-dropped attention kernels of experiments/attention/ and lets the
+# "attention" option (VITDET_ATTN) select them, so that profiles/r02_attention_analysis.md can be reproduced.
+EXPERIMENTS_DIR = os.path.join(os.path.dirname(PKG_DIR), "experiments", "attention")
+EXPERIMENT_SOURCES = ["attention_tc8.cu", "attention_tcp.cu", "attention_tc8p.cu", "attention_pp.cu", "attention_sw.cu", "attention_tc3.cu"]
+
+
+def _with_experiments() -> bool:
+    return os.environ.get("VITDET_BUILD_EXPERIMENTS", "0") == "1"
 
 
 def _nvcc() -> str:
@@ -42,6 +52,11 @@ def _source_hash() -> str:
         with open(path, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    if _with_experiments():
+        h.update(b"experiments")
+        for name in EXPERIMENT_SOURCES:
+            with open(os.path.join(EXPERIMENTS_DIR, name), "rb") as f:
+                h.update(f.read())
     return h.hexdigest()
 
 
@@ -61,10 +76,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     objs = []
-    for src in SOURCES:
+    extra = ["-DVITDET_EXPERIMENTS"] if _with_experiments() else []
+    jobs = [(src, os.path.join(CSRC, src)) for src in SOURCES]
+    if _with_experiments():
+        jobs += [(src, os.path.join(EXPERIMENTS_DIR, src)) for src in EXPERIMENT_SOURCES]
+    for src, path in jobs:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

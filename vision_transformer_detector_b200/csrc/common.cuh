@@ -62,6 +62,17 @@ __device__ __forceinline__ float apply_act(float x) {
     return x;
 }
 
+// Activation of the fp32-accumulate mode's tensor-core epilogues.  Mish keeps the one-ex2 / one-rcp form: ex2.approx and
+// rcp.approx are accurate to 2 and 1 float32 ulp, the form's absolute error is 4e-7 |x| (tests: test_mish_fast_form_accuracy),
+// three orders of magnitude inside the mode's 1e-3 budget, and expf + an IEEE division made the 28 -> 3584 layer's epilogue
+// three times slower.  tanh.approx (2^-11) is NOT good enough for GELU there: tanhf.
+template <int ACT>
+__device__ __forceinline__ float apply_act_f32acc(float x) {
+    if (ACT == ACT_MISH) return mish<false>(x);
+    if (ACT == ACT_GELU) return gelu_tanh<true>(x);
+    return x;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -221,17 +232,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure reported
 // through the C ABI), never as a hung GPU.  try_wait suspends the thread in hardware for a
 // time slice, so the poll count is small on the normal path; the clock is only read after many
-// failed polls.  ~4 s at 2 GHz is far beyond any legitimate wait in these kernels.
+// failed polls.  ~4 s at 2 GHz is far beyond any legitimate wait in these kernels — but clock64 keeps counting
+// while a context is preempted or time-sliced (MPS, a debugger, an oversubscribed GPU), so deployments that share
+// the GPU build with -DVITDET_NO_MBAR_WATCHDOG and get plain unbounded waits.
+#ifndef VITDET_NO_MBAR_WATCHDOG
+#define VITDET_WATCHDOG_CHECK(polls, mask, t0)                        \
+    if ((++polls & (mask)) == 0) {                                    \
+        long long now = clock64();                                    \
+        if (t0 == 0) t0 = now;                                        \
+        else if (now - t0 > 8000000000ll) __trap();                   \
+    }
+#else
+#define VITDET_WATCHDOG_CHECK(polls, mask, t0) (void)polls; (void)t0;
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 0x3fffu) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) __trap();
-        }
+        VITDET_WATCHDOG_CHECK(polls, 0x3fffu, t0)
     }
 }
 
@@ -243,11 +262,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(200);
-        if ((++polls & 0x3ffu) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) __trap();
-        }
+        VITDET_WATCHDOG_CHECK(polls, 0x3ffu, t0)
     }
 }
 

@@ -4,15 +4,18 @@
 //   transformer_preprocessor det.py:239-309 -> transformer_encoder det.py:312-414 -> mlp_head
 //   det.py:417-495 -> transform_predictions det.py:586-647 + thresholds det.py:2257-2283/1359-1384.
 //
-// Data layout in HBM (bf16 mode; the fp32 mode uses the same shapes with f32 elements):
+// Data layout in HBM (bf16 mode; the fp32 mode uses the same shapes with 4 bytes per element: IEEE float32 for the
+// CUDA-core kernels, or two bf16 planes (hi | lo) per buffer for the tensor-core form, see forward_fp32_tc):
 //   x     f32  [B*T, D4]        residual stream, kept in f32 for the whole batch (145 KB / image)
 //   per encoder chunk of Bc images (Mc = Bc*T rows), reused by every chunk:
 //   patch bf16 [Mc, P8]         extract_patches output, (row, col, channel) order
 //   y     bf16 [Mc, D8]         LayerNorm output (A operand of the QKV GEMM / first MLP GEMM)
-//   qkv   bf16 [Mc, 3*H*64]     q | k | v, one 64-wide (128-byte) slot per head, pads are zero
-//   ctx   bf16 [Mc, H*64]       attention output, same head pitch
+//   qkv   bf16 [Mc, 3*H*hp]     q | k | v, hp = key_dim rounded up to 8 elements per head (no 64-wide pad in HBM: the
+//                               attention kernel's 64-column TMA boxes start at column head*hp)
+//   ctx   bf16 [Mc, H*hp]       attention output, same head pitch
 //   u0,u1 bf16 [Mc, w1],[Mc,w2] ping-pong activations of the MLP pyramid
-//   head (whole batch, R = B*S rows): s [B, T*S] == [R, T] (Reshape is a view), h0/h1 [R, u1],[R,u2]
+//   head (whole batch, R = B*S rows): s [R, Tp] (Tp = T rounded up to a 16-byte row pitch; for Tp == T this is the
+//                               compact [B, T*S] buffer of which the reference's Reshape is a view), h0/h1 [R, u1],[R,u2]
 // Weights: every Dense kernel is stored transposed, W[N, K] with K contiguous (both tcgen05 operands
 // are K-major), once in bf16 and once in f32; biases in f32.
 #include <cuda.h>
@@ -56,7 +59,8 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int kMaxKeyDim = 64;    // one 128-byte swizzle row of bf16 per head in shared memory
 // Elements per head in the qkv / ctx matrices: key_dim rounded up to 8 (16-byte rows for TMA and vector stores).  The
-// attention kernel's tensor map zero-fills columns hp..63 of every head tile, so HBM carries no 64-wide pad.
+// attention kernel's 64-column boxes start at column head * hp, so HBM carries no 64-wide pad (Q's spill columns are
+// cleared in shared memory, V's only produce output columns that are never stored).
 static inline int head_pitch(int key_dim) { return (key_dim + 7) / 8 * 8; }
 
 // Run-time switches of one handle (vitdet_set_option); the defaults are the product path unless the environment
@@ -66,7 +70,8 @@ struct Options {
     int fuse_tail = 1;     // VITDET_FUSE_TAIL=0: the last three MLP layers as separate GEMM launches
     int gemm_pair = 1;     // VITDET_GEMM_PAIR=0 never / all (2) wherever legal / default: K >= 512 layers
     int fp32_tc = 1;       // VITDET_FP32=simt: the fp32 mode on CUDA-core IEEE kernels instead of split-bf16 tensor-core GEMMs
-    int attention = 4;     // VITDET_ATTN: 4 one CTA per work item (attention_tc.cu, the fastest measured); experimental forms: 40 persistent, 8 / 80 split score rows, 2 ping-pong, 1 software-pipelined, 3 three CTAs per SM
+    int attention = 4;     // VITDET_ATTN: 4 = attention_tc.cu (the product kernel); builds with VITDET_BUILD_EXPERIMENTS=1 also take
+                           // 40 persistent, 8 / 80 split score rows, 2 ping-pong, 1 software-pipelined, 3 three CTAs per SM
 };
 
 static Options env_options() {
@@ -75,18 +80,24 @@ static Options env_options() {
     if (const char* e = getenv("VITDET_FUSE_TAIL")) o.fuse_tail = strcmp(e, "0") != 0;
     if (const char* e = getenv("VITDET_GEMM_PAIR")) o.gemm_pair = strcmp(e, "0") == 0 ? 0 : (strcmp(e, "all") == 0 ? 2 : 1);
     if (const char* e = getenv("VITDET_FP32")) o.fp32_tc = strcmp(e, "simt") != 0;
+#ifdef VITDET_EXPERIMENTS
     if (const char* e = getenv("VITDET_ATTN")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8 || v == 40 || v == 80) o.attention = v; }
+#endif
     return o;
 }
 
 static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, cudaStream_t st) {
-    if (version == 4) return attn_tc_launch(plan, st);
+#ifdef VITDET_EXPERIMENTS
+    // measured-and-dropped kernels of experiments/attention/ (profiles/r02_attention_analysis.md)
     if (version == 8) return attn_tc8_launch(plan, st);
     if (version == 80) return attn_tc8p_launch(plan, num_sms, st);
     if (version == 2) return attn_pp_launch(plan, num_sms, st);
     if (version == 1) return attn_sw_launch(plan, num_sms, st);
     if (version == 3) return attn_tc3_launch(plan, st);
-    return attn_tcp_launch(plan, num_sms, st);
+    if (version == 40) return attn_tcp_launch(plan, num_sms, st);
+#endif
+    (void)version; (void)num_sms;
+    return attn_tc_launch(plan, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,8 +106,8 @@ static cudaError_t attn_launch(int version, const AttnPlan& plan, int num_sms, c
 // src: Keras Dense kernel viewed as row-major [K, N].  Element (k, n) goes to row rmap(n), column
 // cmap(k) of the transposed, padded destination, where
 //   rmap(n) = row_off + (n / gn) * pn + n % gn      cmap(k) = (k / gk) * pk + k % gk
-// (identity for plain Dense; gn = key_dim, pn = 64 scatters the heads of a q/k/v kernel to their
-// 64-wide slots; gk = key_dim, pk = 64 does the same for the K axis of attention_output).
+// (identity for plain Dense; gn = key_dim, pn = hp scatters the heads of a q/k/v kernel to their hp-wide slots
+// (hp = key_dim rounded up to 8); gk = key_dim, pk = hp does the same for the K axis of attention_output).
 __global__ void pack_dense_kernel(const float* __restrict__ src, int K, int N, int gn, int pn, int row_off, int gk,
                                   int pk, __nv_bfloat16* __restrict__ w16, int ld16, long long lo_off,
                                   float* __restrict__ w32, int ld32) {
@@ -378,6 +389,7 @@ struct vitdet_handle {
     std::map<long long, std::vector<TcGemmPlan>> plans32;    // fp32-accumulate mode on the tensor cores: GEMM plans in launch order, key (B << 20) | chunk
 
     // debug taps (vitdet_debug_taps): residual stream after the patch embedding and after every block, of the last forward
+    bool weights_dirty = false;         // set_weight ran since the last forward: the pack kernels (legacy stream) must finish first
     int s_layout_mode = -1;             // arithmetic mode the slot matrix `s` was last laid out for (its pad columns are zeroed per layout)
     bool taps_on = false;
     DevBuf taps;                        // f32 [(L + 1)][B*T, D4]
@@ -1026,6 +1038,7 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
     if (mode != VITDET_MODE_BF16 && mode != VITDET_MODE_FP32) return fail(VITDET_E_INVALID, "forward: unknown mode %d", mode);
     for (const WeightSlot& s : h->slots)
         if (!s.set) return fail(VITDET_E_UNSET, "forward: weight '%s' has not been set", s.name.c_str());
+    if (h->weights_dirty) { CU_TRY(cudaDeviceSynchronize()); h->weights_dirty = false; }
     const vitdet_config& c = h->cfg;
     const bool bf = mode == VITDET_MODE_BF16;
     if (!bf && h->opt.fp32_tc) return forward_fp32_tc(h, images, B, logits, dpar, det, st, opts);
@@ -1278,7 +1291,9 @@ int vitdet_set_weight(vitdet_handle* h, const char* name_in, const float* data, 
             break;
     }
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaDeviceSynchronize());
+    // no device-wide synchronise per tensor (245 of them for the default model): the staging buffer is reused in stream
+    // order, and the first forward after a weight change synchronises once (weights_dirty)
+    h->weights_dirty = true;
     s.master.assign(data, data + s.count);
     s.set = true;
     return 0;
@@ -1332,7 +1347,14 @@ int vitdet_set_option(vitdet_handle* h, const char* key, int value) {
     else if (k == "fuse_tail") h->opt.fuse_tail = value != 0;
     else if (k == "gemm_pair") { if (value < 0 || value > 2) return fail(VITDET_E_INVALID, "set_option(gemm_pair): 0, 1 or 2"); h->opt.gemm_pair = value; }
     else if (k == "fp32_tc") h->opt.fp32_tc = value != 0;
-    else if (k == "attention") { if (value != 1 && value != 2 && value != 3 && value != 4 && value != 8 && value != 40 && value != 80) return fail(VITDET_E_INVALID, "set_option(attention): 1, 2, 4, 8, 40 or 80"); h->opt.attention = value; }
+    else if (k == "attention") {
+#ifdef VITDET_EXPERIMENTS
+        if (value != 1 && value != 2 && value != 3 && value != 4 && value != 8 && value != 40 && value != 80) return fail(VITDET_E_INVALID, "set_option(attention): 1, 2, 3, 4, 8, 40 or 80");
+#else
+        if (value != 4) return fail(VITDET_E_INVALID, "set_option(attention): this build only holds the product kernel (4); VITDET_BUILD_EXPERIMENTS=1 adds the others");
+#endif
+        h->opt.attention = value;
+    }
     else return fail(VITDET_E_NOT_FOUND, "set_option: unknown option '%s'", key);
     h->enc_plans.clear();
     h->head_plans.clear();

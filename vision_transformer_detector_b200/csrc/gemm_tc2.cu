@@ -21,6 +21,9 @@ namespace vitdet {
 
 namespace {
 
+template <int ACT, bool F32ACC>
+__device__ __forceinline__ float act_out(float x) { return F32ACC ? apply_act_f32acc<ACT>(x) : apply_act<ACT, false>(x); }
+
 constexpr int kBM = 128;              // UMMA M (cta_group::1)
 constexpr int kBK = 64;               // one 128-byte swizzle row of bf16
 constexpr int kUK = 16;               // UMMA K for 16-bit inputs
@@ -225,10 +228,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int g = 0; g < 4; ++g) {
                                 const int c = c0 + 16 * hh + 4 * g;
                                 const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(bs + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                y16[4 * g + 0] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 0]) + b4.x + pos_v);
-                                y16[4 * g + 1] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 1]) + b4.y + pos_v);
-                                y16[4 * g + 2] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 2]) + b4.z + pos_v);
-                                y16[4 * g + 3] = apply_act<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
+                                y16[4 * g + 0] = act_out<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 0]) + b4.x + pos_v);
+                                y16[4 * g + 1] = act_out<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 1]) + b4.y + pos_v);
+                                y16[4 * g + 2] = act_out<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 2]) + b4.z + pos_v);
+                                y16[4 * g + 3] = act_out<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
                             }
                             store_f32_half_chunk_coalesced(s_tile, y16, lane, m0 + quad * 32, p.M, reinterpret_cast<float*>(p.out), p.ldc,
                                                            p.resid, p.ldr, n0 + c0 + 16 * hh);
@@ -258,7 +261,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float y = apply_act<ACT, PRECISE>(x[j] + pos_v) + r[j];
+                                const float y = act_out<ACT, PRECISE>(x[j] + pos_v) + r[j];
                                 x[j] = (full || n + j < p.N) ? y : 0.f;
                             }
                             *reinterpret_cast<float4*>(orow + n) = make_float4(x[0], x[1], x[2], x[3]);
@@ -280,8 +283,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const int n = n0 + c0 + 2 * g;
                             const float bb0 = (p.bias && n < p.N) ? __ldg(bs + c0 + 2 * g) : 0.f;
                             const float bb1 = (p.bias && n + 1 < p.N) ? __ldg(bs + c0 + 2 * g + 1) : 0.f;
-                            float y0 = apply_act<ACT, PRECISE>(__uint_as_float(v[2 * g + 0]) + bb0);
-                            float y1 = apply_act<ACT, PRECISE>(__uint_as_float(v[2 * g + 1]) + bb1);
+                            float y0 = apply_act_f32acc<ACT>(__uint_as_float(v[2 * g + 0]) + bb0);
+                            float y1 = apply_act_f32acc<ACT>(__uint_as_float(v[2 * g + 1]) + bb1);
                             if (n >= p.N) y0 = 0.f;
                             if (n + 1 >= p.N) y1 = 0.f;
                             const __nv_bfloat162 hi = __floats2bfloat162_rn(y0, y1);

@@ -124,12 +124,14 @@ struct AttnPlan {
 };
 int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d);
 cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream);     // tcgen05 kernel, one softmax thread per query row (attention_tc.cu)
-cudaError_t attn_tc8_launch(const AttnPlan& plan, cudaStream_t stream);    // tcgen05 kernel, score rows split over warp pairs (attention_tc8.cu)
-cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);   // persistent form of attention_tc.cu (attention_tcp.cu)
-cudaError_t attn_sw_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent, software-pipelined softmax warps (attention_sw.cu)
-cudaError_t attn_tc3_launch(const AttnPlan& plan, cudaStream_t stream);    // 64-key tiles, three CTAs per SM (attention_tc3.cu)
-cudaError_t attn_pp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);    // persistent ping-pong: two work streams per CTA take turns on the SFU (attention_pp.cu)
-cudaError_t attn_tc8p_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);  // persistent + split score rows (attention_tc8p.cu)
+#ifdef VITDET_EXPERIMENTS      // experiments/attention/: measured and dropped (profiles/r02_attention_analysis.md)
+cudaError_t attn_tc8_launch(const AttnPlan& plan, cudaStream_t stream);
+cudaError_t attn_tc3_launch(const AttnPlan& plan, cudaStream_t stream);
+cudaError_t attn_tcp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);
+cudaError_t attn_tc8p_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);
+cudaError_t attn_pp_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);
+cudaError_t attn_sw_launch(const AttnPlan& plan, int num_sms, cudaStream_t stream);
+#endif
 cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream);
 // fp32-accumulate mode on the tensor cores (attention_tcs.cu): plan.desc.qkv / ctx are the hi planes, tm_lo the tensor map
 // of the lo plane of qkv (same shape and pitch), ctx_lo the lo plane of the context rows.

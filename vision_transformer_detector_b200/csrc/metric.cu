@@ -492,6 +492,9 @@ int vitdet_map_reset(vitdet_map* m, void* stream) {
     CU_TRY(cudaMemsetAsync(m->labels.p, 0, m->labels.bytes, st));
     CU_TRY(cudaMemsetAsync(m->head.p, 0, m->head.bytes, st));
     CU_TRY(cudaMemsetAsync(m->showed.p, 0, m->showed.bytes, st));
+    // the host-array entry points run on the legacy stream: without this a reset issued on a non-blocking stream could
+    // still be in flight when the next vitdet_map_update_host starts
+    CU_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 

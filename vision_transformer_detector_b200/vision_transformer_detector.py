@@ -257,8 +257,14 @@ def _decode_params(objectness_threshold, classification_threshold, strict, image
 
 
 def _is_uint8(x) -> bool:
-    """uint8 pixels (numpy or torch): normalised x / 127.5 - 1 inside the patch kernel (utilities.py:446-447)."""
     return str(getattr(x, "dtype", "")).endswith("uint8")
+
+
+def _pixels(x, normalize_uint8: bool) -> bool:
+    """True when `x` holds uint8 pixels AND the caller asked for the fused input normalisation x / 127.5 - 1
+    (vision_transformer_utilities.py:446-447, done inside the patch kernel).  Without the flag a uint8 array is only cast
+    to float32, which is what keras Model.predict does with it."""
+    return bool(normalize_uint8) and _is_uint8(x)
 
 
 def _is_torch_cuda(x) -> bool:
@@ -449,8 +455,12 @@ class MeanAveragePrecision:
     reset_states = reset_state      # keras' older spelling
 
     def _stream(self) -> C.c_void_p:
-        import torch
-        return _torch_stream_ptr(torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else C.c_void_p()
+        # numpy-only callers never import torch: the legacy stream (NULL), which is also what the *_host entry points use
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is None or not torch.cuda.is_available():
+            return C.c_void_p()
+        return _torch_stream_ptr(torch.device("cuda", torch.cuda.current_device()))
 
     def _state(self):
         bboxes = np.zeros((self.classes, self.latest_related_images, self.bboxes_per_image, 2), np.float32)
@@ -685,17 +695,19 @@ class VisionTransformerDetector:
         return int(shape[0])
 
     def detect(self, x, objectness_threshold=None, classification_threshold=None, strict=True, image_size=None,
-               compute_mode: str | None = None, packed: bool = False) -> DetectionRecords:
+               compute_mode: str | None = None, packed: bool = False, normalize_uint8: bool = False) -> DetectionRecords:
         """predict + transform_predictions + thresholds in one call (the decode is fused into the
         head's last Dense).  image_size defaults to the model's own input size.  packed=True also returns the
-        (B*17, 13) float32 record block that the multi-GPU gather exchanges (parallel.RECORD_WIDTH)."""
+        (B*17, 13) float32 record block that the multi-GPU gather exchanges (parallel.RECORD_WIDTH).
+        normalize_uint8=True: `x` holds uint8 pixels, normalised x / 127.5 - 1 inside the patch kernel (a quarter of the
+        float32 copy); by default a uint8 array is cast to float32 like any other dtype, as Keras does."""
         B = self._check_images(x.shape)
         S = Constants.MAX_DETECT_OBJECTS_QUANTITY.value
         if image_size is None:
             image_size = self.config.input_shape[:2]
         params = _decode_params(objectness_threshold, classification_threshold, strict, image_size)
         mode = self._mode(compute_mode)
-        u8 = _is_uint8(x)
+        u8 = _pixels(x, normalize_uint8)
         if _is_torch_cuda(x):
             import torch
             xi = x.contiguous() if u8 else x.to(torch.float32).contiguous()
@@ -720,7 +732,7 @@ class VisionTransformerDetector:
         return DetectionRecords(logits, dec, cid, cc, keep, cor, pk)
 
     def submit(self, x, objectness_threshold=None, classification_threshold=None, strict=True, image_size=None,
-               compute_mode: str | None = None, packed: bool = False) -> int:
+               compute_mode: str | None = None, packed: bool = False, normalize_uint8: bool = False) -> int:
         """Asynchronous detect() for HOST arrays (vitdet_submit_host): stages and copies `x`, enqueues forward + decode +
         read-back and returns a ticket for collect().  Two submissions may be in flight; the copy of the second overlaps
         the compute of the first.  A page-locked `x` must stay alive until its ticket is collected."""
@@ -728,7 +740,7 @@ class VisionTransformerDetector:
         if image_size is None:
             image_size = self.config.input_shape[:2]
         params = _decode_params(objectness_threshold, classification_threshold, strict, image_size)
-        u8 = _is_uint8(x)
+        u8 = _pixels(x, normalize_uint8)
         xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         ticket = C.c_int(-1)
         _capi.check(self._lib.vitdet_submit_host(self._h, _capi.np_ptr(xi), 1 if u8 else 0, B, self._mode(compute_mode), C.byref(params),
@@ -747,14 +759,14 @@ class VisionTransformerDetector:
         _capi.check(self._lib.vitdet_collect(self._h, int(ticket), _capi.np_ptr(logits), C.byref(st)))
         return DetectionRecords(logits, dec, cid, cc, keep, cor, pk)
 
-    def predict(self, x, batch_size=None, verbose="auto", steps=None, callbacks=None, **kwargs):
+    def predict(self, x, batch_size=None, verbose="auto", steps=None, callbacks=None, normalize_uint8: bool = False, **kwargs):
         """keras Model.predict: host array in, numpy (B, 17, 6) raw logits out.  `batch_size` only
         chunks the work in Keras; here the engine's own encoder micro-batch bounds memory, so it is
-        accepted and ignored."""
+        accepted and ignored.  normalize_uint8: see detect()."""
         if _is_torch_cuda(x):
-            return self(x).cpu().numpy()
+            return self(x, normalize_uint8=normalize_uint8).cpu().numpy()
         B = self._check_images(np.shape(x))
-        u8 = _is_uint8(x)      # raw pixels: normalised on the device, a quarter of the float32 copy
+        u8 = _pixels(x, normalize_uint8)
         xi = np.ascontiguousarray(x) if u8 else np.ascontiguousarray(np.asarray(x, dtype=np.float32))
         logits = np.empty((B, Constants.MAX_DETECT_OBJECTS_QUANTITY.value, 6), np.float32)
         params = _decode_params(None, None, True, self.config.input_shape[:2])
@@ -762,16 +774,16 @@ class VisionTransformerDetector:
         _capi.check(fn(self._h, _capi.np_ptr(xi), B, self._mode(), C.byref(params), _capi.np_ptr(logits), None, None))
         return logits
 
-    def __call__(self, x, training=False, compute_mode: str | None = None):
+    def __call__(self, x, training=False, compute_mode: str | None = None, normalize_uint8: bool = False):
         """model(x, training=False): torch CUDA tensor in -> torch CUDA tensor out (asynchronous on
         torch's current stream); numpy in -> numpy out."""
         if training:
             raise NotImplementedError("training=True is outside the predict/decode path")
         if not _is_torch_cuda(x):
-            return self.predict(x)
+            return self.predict(x, normalize_uint8=normalize_uint8)
         import torch
         B = self._check_images(x.shape)
-        u8 = _is_uint8(x)
+        u8 = _pixels(x, normalize_uint8)
         xi = x.contiguous() if u8 else x.to(torch.float32).contiguous()
         with torch.cuda.device(xi.device):
             logits = torch.empty((B, Constants.MAX_DETECT_OBJECTS_QUANTITY.value, 6), dtype=torch.float32, device=xi.device)
