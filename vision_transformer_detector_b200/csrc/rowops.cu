@@ -7,9 +7,6 @@
 #include "kernels.h"
 #include "launch.h"
 
-#include <cstdlib>
-#include <cstring>
-
 namespace vitdet {
 
 namespace {
@@ -41,6 +38,8 @@ template <> struct OutT<__nv_bfloat16> {
 // every run starts 8-byte aligned and is written with 4-element vector stores (the projection weight is
 // packed with the same zero columns); rp = 3p gives the reference's dense 3p^2 vector.
 // One block per (image, token row of the grid).
+// Measured and dropped (r02): staging every image row through shared memory with coalesced 16-byte loads and bank-conflict-
+// free reads — 0.135 ms against this kernel's 0.118 ms per 64 images (latency-bound at 28 % occupancy, 59 KB of row buffers).
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Vec4Store;
 template <> struct Vec4Store<float> {
@@ -103,73 +102,6 @@ patchify_kernel(const IN* __restrict__ img, int H, int W, int p, int gh, int gw,
                     const int x3 = x0 + q - 3 * pad_left;
                     OutT<T>::st(dst + q, (y_ok && q < run && x3 >= 0 && x3 < W3) ? ld_pixel(src + x0 + q) : 0.f);
                 }
-            }
-        }
-    }
-    const int P = rp * p;
-    if (ldp > P) {
-        const int padw = ldp - P;
-        for (int px = warp; px < gw; px += 8)
-            for (int w = lane; w < padw; w += 32) OutT<T>::st(out + (tok0 + px) * ldp + P + w, 0.f);
-    }
-}
-
-// Same result, staged through shared memory: one warp takes one image row of the block's token row, pulls it in with
-// fully coalesced 16-byte loads (the scalar loads above touch every 128-byte line of the row four times: the kernel sat at
-// 45 % of DRAM bandwidth, LSU-bound), and writes the p-runs of all tokens of that row from its private row buffer.
-// Needs 16-byte aligned image rows (3 W elements a multiple of 16 bytes) and rp % 4 == 0; the launcher falls back otherwise.
-template <typename T, typename IN>
-__global__ void __launch_bounds__(256)
-patchify_rows_kernel(const IN* __restrict__ img, int H, int W, int p, int gh, int gw, int pad_top, int pad_left,
-                     T* __restrict__ out, int ldp, int rp, int row_buf /* floats per warp buffer */) {
-    extern __shared__ __align__(16) float srow[];
-    pdl_launch_dependents();
-    pdl_wait();
-    const int py = blockIdx.x, b = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int run = 3 * p, W3 = 3 * W, lead = 3 * pad_left;
-    const size_t tok0 = (static_cast<size_t>(b) * gh + py) * gw;
-    float* buf = srow + warp * row_buf;             // [lead zeros | W3 pixels | zeros up to gw * run + 4]
-    const int padded = gw * run + 4;
-    constexpr int kPerVec = 16 / static_cast<int>(sizeof(IN));      // source elements per 16-byte load
-    for (int r = warp; r < p; r += 8) {
-        const int y = py * p + r - pad_top;
-        const bool y_ok = (y >= 0) && (y < H);
-        __syncwarp();
-        if (y_ok) {
-            const IN* src = img + (static_cast<size_t>(b) * H + y) * W3;
-            for (int i = lane; i < lead; i += 32) buf[i] = 0.f;
-            for (int i = lead + W3 + lane; i < padded; i += 32) buf[i] = 0.f;
-            for (int v = lane; v < W3 / kPerVec; v += 32) {
-                if (sizeof(IN) == 4) {
-                    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + v);
-                    float* d = buf + lead + 4 * v;
-                    d[0] = f.x; d[1] = f.y; d[2] = f.z; d[3] = f.w;
-                } else {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + v);
-                    const uint8_t* pb = reinterpret_cast<const uint8_t*>(&u);
-                    float* d = buf + lead + 16 * v;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) d[j] = __fsub_rn(__fdiv_rn(static_cast<float>(pb[j]), 127.5f), 1.f);
-                }
-            }
-        } else {
-            for (int i = lane; i < padded; i += 32) buf[i] = 0.f;
-        }
-        __syncwarp();
-        // 4 tokens x 8 four-element groups per warp pass: with an odd run length (3p = 51) the 32 lanes' shared-memory
-        // addresses px * run + 4 q + j fall into 32 different banks, and every token gets a 64-byte store segment
-        const int gpr = rp >> 2;                     // 4-element store groups per run
-        const int tl = lane >> 3, ql = lane & 7;
-        for (int px = tl; px < gw; px += 4) {
-            T* drow = out + (tok0 + px) * ldp + r * rp;
-            for (int q = ql; q < gpr; q += 8) {
-                const int w = 4 * q;
-                const float* sp = buf + px * run + w;
-                float v4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v4[j] = (w + j < run) ? sp[j] : 0.f;
-                Vec4Store<T>::st(drow + w, v4[0], v4[1], v4[2], v4[3]);
             }
         }
     }
@@ -478,24 +410,6 @@ static cudaError_t patchify_launch_t(const IN* images, int B, int H, int W, int 
     const size_t smem = 0;
     // vector stores need every run (and every token row) to start on a 4-element boundary
     const bool vec = (rp % 4 == 0) && (ldp % 4 == 0) && ((reinterpret_cast<uintptr_t>(patches) & 15) == 0);
-    // row-staged kernel: image rows must be 16-byte aligned; VITDET_PATCHIFY=direct keeps the scalar-load kernel (A/B)
-    static int staged = -1;
-    if (staged < 0) { const char* e = getenv("VITDET_PATCHIFY"); staged = (e && strcmp(e, "direct") == 0) ? 0 : 1; }
-    const int row_buf = (gw * 3 * p + 4 + 3) / 4 * 4;
-    const size_t smem_rows = static_cast<size_t>(8) * row_buf * sizeof(float);
-    if (staged && vec && ((static_cast<size_t>(3) * W * sizeof(IN)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(images) & 15) == 0) &&
-        smem_rows <= 200 * 1024) {
-        if (out_f32) {
-            auto k = patchify_rows_kernel<float, IN>;
-            cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024);      // set once per kernel: the limit, not this call's size
-            if (e != cudaSuccess) return e;
-            return launch_kernel(k, grid, dim3(256), smem_rows, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, static_cast<float*>(patches), ldp, rp, row_buf);
-        }
-        auto k = patchify_rows_kernel<__nv_bfloat16, IN>;
-        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(k), 200 * 1024);      // set once per kernel: the limit, not this call's size
-        if (e != cudaSuccess) return e;
-        return launch_kernel(k, grid, dim3(256), smem_rows, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, static_cast<__nv_bfloat16*>(patches), ldp, rp, row_buf);
-    }
     if (out_f32) {
         float* o = static_cast<float*>(patches);
         if (vec) return launch_kernel(patchify_kernel<float, true, IN>, grid, dim3(256), smem, stream, 1, images, H, W, p, gh, gw, pad_top, pad_left, o, ldp, rp);
