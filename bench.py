@@ -396,7 +396,7 @@ def attention_roofline(cfg, B, steps, prof, ms_step_total, pk, clocks):
     flops = 4.0 * H * T * T * d * L * images
     ex2 = 1.0 * H * T * T * L * images
     tf = flops / (ms_k * 1e-3) / 1e12
-    out = {"kernel": "attn_tc8p_kernel / attn_tcp_kernel (persistent flash attention, S/P/O in TMEM)", "launches": n_k, "avg_launch_ms": ms_k / n_k,
+    out = {"kernel": "attn_tc_kernel (flash attention on tcgen05, S / P / O in TMEM, 128 queries x 1 head per CTA, 2 CTAs per SM)", "launches": n_k, "avg_launch_ms": ms_k / n_k,
            "share_of_step": ms_k / ms_step_total, "tensor": {"achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"]},
            "note": "at head_dim 40 one score costs 160 tensor FLOP and one SFU ex2: the SFU (16/clk/SM) needs ~2.3x the tensor pipe's time, so it is the binding unit"}
     mhz = (clocks or {}).get("sm_mhz")
@@ -437,12 +437,13 @@ def run_ours(args):
         if os.path.exists(tpath) and args.variant == "default":
             tj = json.load(open(tpath))
             from vision_transformer_detector_b200 import build as _b
-            # dram bytes of one launch from the committed `ncu --set full` capture; only quoted for the source tree it was
-            # taken on (scripts/gpu_ncu_traffic.sh stamps the capture with the csrc hash) and the same rows per launch
-            if tj.get("csrc_hash") == _b._source_hash() and tj.get("rows_per_launch") == roofline["algorithmic_flop_per_launch"] / (2.0 * 3584 * 1792):
+            # dram bytes of one launch from the committed `ncu --set full` capture; only quoted for the kernel sources it was
+            # taken on (scripts/summarize_profiles.py stamps the capture with the hash of gemm_tc2.cu + the headers it
+            # includes + the nvcc flags, written on the box by the visit that took the capture) and the same rows per launch
+            if tj.get("kernel_hash") == _b.kernel_hash() and tj.get("rows_per_launch") == roofline["algorithmic_flop_per_launch"] / (2.0 * 3584 * 1792):
                 roofline["traffic"] = tj.get("traffic_bytes_per_launch")
             else:
-                roofline["traffic_note"] = "profiles/gemm_mlp_2_traffic.json was captured on another source tree / launch size: not quoted"
+                roofline["traffic_note"] = "profiles/gemm_mlp_2_traffic.json was captured on other kernel sources / another launch size: not quoted"
     roof_attn = attention_roofline(cfg, B, args.steps, prof_a, ms_total_a, pk, clocks_a) if args.mode == "bf16" else None
     if roof_attn is not None:
         roof_attn["timing"] = "second pass of the same K steps with engine events around the attention launches only"

@@ -5,6 +5,9 @@ rm -f $O/*.ncu-rep
 python -c "
 import sys; sys.path.insert(0, '.')
 from vision_transformer_detector_b200 import build as b; print(b._source_hash())" > $O/csrc_hash.txt
+python -c "
+import sys; sys.path.insert(0, '.')
+from vision_transformer_detector_b200 import build as b; print(b.kernel_hash())" > $O/kernel_hash.txt
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; tail -4 $O/pytest_gpu.log
 timeout 600 python __graft_entry__.py smoke > $O/smoke.log 2>&1; tail -5 $O/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 --breakdown > $O/bench_n1.json 2> $O/bench_n1.err; cut -c1-300 $O/bench_n1.json; tail -3 $O/bench_n1.err

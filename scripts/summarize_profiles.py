@@ -95,8 +95,9 @@ def traffic(tag):
            "dram_bytes_write": val("dram__bytes_write.sum"), "source": f"profiles/{tag}_ncu_gemm.md (ncu --set full, B = 64)"}
     out["traffic_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
     # stamp: bench.py quotes the figure only for the source tree and launch size it was captured on
-    hp = os.path.join(OUT, "csrc_hash.txt")
-    out["csrc_hash"] = open(hp).read().strip() if os.path.exists(hp) else None
+    hp = os.path.join(OUT, "kernel_hash.txt")
+    out["kernel_hash"] = open(hp).read().strip() if os.path.exists(hp) else None
+    out["kernel_hash_of"] = "gemm_tc2.cu common.cuh kernels.h launch.h + nvcc flags (vision_transformer_detector_b200.build.kernel_hash)"
     out["rows_per_launch"] = 64 * 1296
     with open(os.path.join(PROF, "gemm_mlp_2_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)

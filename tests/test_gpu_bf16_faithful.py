@@ -173,7 +173,8 @@ def test_mlp_tail_kernel(M, widths, with_ln, act):
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
-@pytest.mark.parametrize("B,T,D,S", [(2, 1296, 28, 17), (3, 36, 28, 17), (2, 25, 28, 17), (1, 1600, 768, 17), (2, 7, 12, 5)])
+@pytest.mark.parametrize("B,T,D,S", [(2, 1296, 28, 17), (3, 36, 28, 17), (2, 25, 28, 17), (1, 1600, 768, 17), (2, 7, 12, 5),
+                                     (2, 101, 768, 17), (1, 50, 64, 32), (3, 333, 132, 17)])
 def test_head_slots_kernel(B, T, D, S, mode):
     """Dense(D -> 17) per token + Reshape((17, -1)) (det.py:454-463): the flat reinterpretation, incl. token counts that
     are not a multiple of the 16-byte row pitch (rows padded in memory, invisible at the boundary)."""

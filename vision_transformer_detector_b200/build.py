@@ -60,6 +60,21 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+# Sources that define the dominant GEMM (gemm_tc2_kernel and what it includes): the ncu traffic capture quoted by bench.py's
+# roofline.traffic is stamped with this hash, so that edits to unrelated kernels do not void it.
+DOMINANT_KERNEL_SOURCES = ["gemm_tc2.cu", "common.cuh", "kernels.h", "launch.h"]
+
+
+def kernel_hash(names=None) -> str:
+    h = hashlib.sha256()
+    for name in (names or DOMINANT_KERNEL_SOURCES):
+        h.update(name.encode())
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_current() -> bool:
     if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return False
@@ -77,6 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     objs = []
     extra = ["-DVITDET_EXPERIMENTS"] if _with_experiments() else []
+    # A/B builds (scripts/gpu_ab_lib.sh): extra -D switches; such a build is never stamped as current
+    extra += os.environ.get("VITDET_EXTRA_NVCC_FLAGS", "").split()
     jobs = [(src, os.path.join(CSRC, src)) for src in SOURCES]
     if _with_experiments():
         jobs += [(src, os.path.join(EXPERIMENTS_DIR, src)) for src in EXPERIMENT_SOURCES]
@@ -103,7 +120,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     with open(STAMP_PATH, "w") as f:
-        f.write(_source_hash())
+        f.write(_source_hash() if not os.environ.get("VITDET_EXTRA_NVCC_FLAGS") else "ab-build")
     return LIB_PATH
 
 

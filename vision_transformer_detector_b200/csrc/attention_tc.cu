@@ -81,6 +81,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
         for (int i = 0; i < 32; ++i)
             if (32 * (NCH - 1) + i >= valid) v[NCH - 1][i] = 0xff800000u;     // -inf: keys past the end of the image
     }
+    // (three-input FMNMX3 maxima, 64 instead of 128 instructions, changed nothing: 2.776 vs 2.778 ms per step, r03b_ab.log)
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int c = 0; c < NCH; ++c)

@@ -111,6 +111,9 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 // Measured and dropped (profiles/r02_experiments.md): a one-SFU form — reciprocal of n^2 + 2n + 2 from an integer seed and
 // three packed Newton steps on the FMA pipe, float32-accurate — made the 28 -> 3584 layer SLOWER (1.39 -> 1.48 ms per
 // step): that epilogue is bound by instruction issue, not by the SFU, and the form costs 8 instead of 6.5 slots per element.
+// Also measured and dropped (r03, gpurun_out/r03a_ab.log): ONE reciprocal per pair, 1 / (q0 q1), and two multiplications
+// (1.5 SFU operations per element): 1.381 -> 1.341 ms per step on that layer although ncu has its XU pipe at 85 % — not worth
+// two more roundings in the activation.
 __device__ __forceinline__ uint64_t mish2_fast(uint64_t x) {
     float t0, t1, n0, n1, q0, q1, r0, r1;
     f2_unpack(f2_mul(x, f2_pack(1.4426950408889634f, 1.4426950408889634f)), t0, t1);

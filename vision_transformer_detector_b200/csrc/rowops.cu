@@ -2,6 +2,8 @@
 // projection, and the fused head tail (Dense(U->6) + sigmoid + clip + scale + thresholds).
 // All of them are HBM/L2 streaming kernels: coalesced 16-byte accesses where the layout allows it,
 // warp-shuffle reductions, no shared-memory staging (there is no reuse to exploit).
+#include <algorithm>
+
 #include "boxops.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -41,6 +43,11 @@ template <> struct OutT<__nv_bfloat16> {
 // Measured and dropped (r02): staging every image row through shared memory with coalesced 16-byte loads and bank-conflict-
 // free reads — 0.135 ms against this kernel's 0.118 ms per 64 images (latency-bound at 28 % occupancy, 59 KB of row buffers).
 // ------------------------------------------------------------------------------------------------
+#ifndef VITDET_PATCH_UNROLL
+#define VITDET_PATCH_UNROLL 9
+#endif
+constexpr int kPatchRowUnroll = VITDET_PATCH_UNROLL;     // patch rows a lane loads before it stores (1 = the r-outer loop)
+
 template <typename T> struct Vec4Store;
 template <> struct Vec4Store<float> {
     static __device__ __forceinline__ void st(float* p, float a, float b, float c, float d) {
@@ -81,6 +88,41 @@ patchify_kernel(const IN* __restrict__ img, int H, int W, int p, int gh, int gw,
     const int lpr_shift = (VEC && gpr <= 16) ? 4 : 5;      // lanes per run: 16 or 32
     const int runs_per_warp = 32 >> lpr_shift;
     const int sub = lane >> lpr_shift, q0 = lane & ((1 << lpr_shift) - 1);
+    if (VEC && kPatchRowUnroll > 1) {
+        // A lane keeps its (token, 4-element group) and walks the patch rows, kPatchRowUnroll rows at a time: the 4 x U
+        // loads of a step are independent, so a thread has 16 x U bytes in flight instead of 16 (the kernel is bound by
+        // the read bytes in flight per SM, not by the LSU).
+        const int y_first = py * p - pad_top;
+        const IN* img_b = img + static_cast<size_t>(b) * H * W3 - 3 * pad_left;
+        // work item = (token, group) flattened over the block (468 items on 256 threads for the default model: 91 % of the
+        // lanes busy instead of 61 % with 16 lanes per run); one division per item, outside the row loop
+        const int items = gw * gpr;
+        for (int idx = threadIdx.x; idx < items; idx += 256) {
+            const int px = idx / gpr, q = idx - px * gpr;
+            const int x0 = px * run, w = 4 * q;
+            T* dst_tok = out + (tok0 + px) * ldp + w;
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x3 = x0 + w + j - 3 * pad_left;
+                ok[j] = (w + j < run) && x3 >= 0 && x3 < W3;
+            }
+            for (int r0 = 0; r0 < p; r0 += kPatchRowUnroll) {
+                float v[kPatchRowUnroll][4];
+#pragma unroll
+                for (int u = 0; u < kPatchRowUnroll; ++u) {
+                    const int y = y_first + r0 + u;
+                    const bool y_ok = (r0 + u < p) && (y >= 0) && (y < H);
+                    const IN* src = img_b + static_cast<size_t>(y_ok ? y : 0) * W3 + x0 + w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[u][j] = (y_ok && ok[j]) ? ld_pixel(src + j) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kPatchRowUnroll; ++u)
+                    if (r0 + u < p) Vec4Store<T>::st(dst_tok + (r0 + u) * rp, v[u][0], v[u][1], v[u][2], v[u][3]);
+            }
+        }
+    } else
     for (int r = 0; r < p; ++r) {
         const int y = py * p + r - pad_top;
         const bool y_ok = (y >= 0) && (y < H);
@@ -168,6 +210,7 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
     const float rstd = rsqrtf(sq / static_cast<float>(D) + eps);
 
     if (!row_ok) return;
+    const bool vec_gb = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
     T* yr = y + static_cast<size_t>(row) * ldy;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
@@ -175,10 +218,17 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
         if (e < ldy) {       // pad columns [D, ldy) are written as zero
             float o[4];
             const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            if (vec_gb && e + 4 <= D) {
+                // wide rows: gamma / beta as one 16-byte load each (8 scalar loads per group made the D = 768 kernel LSU-bound)
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + e)), b4 = __ldg(reinterpret_cast<const float4*>(beta + e));
+                o[0] = (xv[0] - mean) * rstd * g4.x + b4.x; o[1] = (xv[1] - mean) * rstd * g4.y + b4.y;
+                o[2] = (xv[2] - mean) * rstd * g4.z + b4.z; o[3] = (xv[3] - mean) * rstd * g4.w + b4.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                o[j] = 0.f;
-                if (e + j < D) o[j] = (xv[j] - mean) * rstd * __ldg(gamma + e + j) + __ldg(beta + e + j);
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = 0.f;
+                    if (e + j < D) o[j] = (xv[j] - mean) * rstd * __ldg(gamma + e + j) + __ldg(beta + e + j);
+                }
             }
             OutT<T>::st4(yr + e, o[0], o[1], o[2], o[3]);
         }
@@ -223,6 +273,68 @@ head_slots_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
         o = (img * S + f / tokens) * ldo + f % tokens;
     }
     OutT<T>::st(out + o, acc + __ldg(bias + s));
+}
+
+// Wide residual streams (embedding_dim >= 64, e.g. the 768-wide variant): the thread-per-(token, slot) kernel above makes
+// every thread walk a whole 3 KB row with 16 bytes in flight (0.70 ms per 32 images at D = 768).  Here a warp owns two
+// tokens at a time: the lanes split the row (coalesced 16-byte loads, all in flight at once), every lane accumulates its
+// share of all S slot products against a shared-memory copy of the [S, D] kernel (each 16-byte weight read serves both
+// tokens), and S butterfly reductions finish the sums.  S is a template parameter so that the accumulators stay in registers.
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+head_slots_wide_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias, int M,
+                       int D, int tokens, int ldo, T* __restrict__ out) {
+    extern __shared__ __align__(16) float hs_smem[];       // [S][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D4 = D >> 2;
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < S * D4; i += 256)        // weights do not depend on the previous kernel
+        reinterpret_cast<float4*>(hs_smem)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    pdl_wait();
+    __syncthreads();
+    const float b = lane < S ? __ldg(bias + lane) : 0.f;
+    const long long per_image = static_cast<long long>(tokens) * S;
+    for (int m0 = 2 * (blockIdx.x * 8 + warp); m0 < M; m0 += 2 * gridDim.x * 8) {
+        const bool two = m0 + 1 < M;
+        const float4* x0 = reinterpret_cast<const float4*>(x + static_cast<size_t>(m0) * ldx);
+        const float4* x1 = reinterpret_cast<const float4*>(x + static_cast<size_t>(two ? m0 + 1 : m0) * ldx);
+        float acc0[S], acc1[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { acc0[s] = 0.f; acc1[s] = 0.f; }
+#pragma unroll 2
+        for (int c = lane; c < D4; c += 32) {
+            const float4 a0 = x0[c], a1 = x1[c];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const float4 ws = reinterpret_cast<const float4*>(hs_smem)[s * D4 + c];
+                acc0[s] = fmaf(a0.x, ws.x, fmaf(a0.y, ws.y, fmaf(a0.z, ws.z, fmaf(a0.w, ws.w, acc0[s]))));
+                acc1[s] = fmaf(a1.x, ws.x, fmaf(a1.y, ws.y, fmaf(a1.z, ws.z, fmaf(a1.w, ws.w, acc1[s]))));
+            }
+        }
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float v0 = acc0[s], v1 = acc1[s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            }
+            if (lane == s) { r0 = v0; r1 = v1; }
+        }
+        if (lane < S) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (t == 1 && !two) break;
+                long long o = static_cast<long long>(m0 + t) * S + lane;
+                if (ldo != tokens) {
+                    const long long img = o / per_image, f = o - img * per_image;
+                    o = (img * S + f / tokens) * ldo + f % tokens;
+                }
+                OutT<T>::st(out + o, (t ? r1 : r0) + b);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -443,6 +555,24 @@ cudaError_t head_slots_launch(const float* x, int ldx, const float* w, const flo
     const long long total = static_cast<long long>(M) * S;
     const int grid = static_cast<int>((total + 255) / 256);
     if (tokens <= 0 || ldo < tokens || M % tokens) return cudaErrorInvalidValue;
+    // the reference's head has 17 slots (det.py:454); other slot counts take the generic kernel
+    const size_t wide_smem = static_cast<size_t>(S) * D * sizeof(float);
+    static const bool wide_ok = !(getenv("VITDET_SLOTS_WIDE") && strcmp(getenv("VITDET_SLOTS_WIDE"), "0") == 0);     // A/B switch
+    if (wide_ok && S == 17 && D >= 64 && (D & 3) == 0 && (ldx & 3) == 0 && wide_smem <= 200u * 1024u &&
+        (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int wgrid = std::min((M + 15) / 16, 2 * 148);
+        cudaError_t e;
+        if (out_f32) {
+            e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(head_slots_wide_kernel<float, 17>), static_cast<int>(wide_smem));
+            if (e != cudaSuccess) return e;
+            return launch_kernel(head_slots_wide_kernel<float, 17>, dim3(wgrid), dim3(256), wide_smem, stream, 1, x, ldx, w, bias, M, D, tokens,
+                                 ldo, static_cast<float*>(out));
+        }
+        e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(head_slots_wide_kernel<__nv_bfloat16, 17>), static_cast<int>(wide_smem));
+        if (e != cudaSuccess) return e;
+        return launch_kernel(head_slots_wide_kernel<__nv_bfloat16, 17>, dim3(wgrid), dim3(256), wide_smem, stream, 1, x, ldx, w, bias, M, D,
+                             tokens, ldo, static_cast<__nv_bfloat16*>(out));
+    }
     if (out_f32)
         return launch_kernel(head_slots_kernel<float>, dim3(grid), dim3(256), 0, stream, 1, x, ldx, w, bias, total, D, S, tokens, ldo,
                              static_cast<float*>(out));
