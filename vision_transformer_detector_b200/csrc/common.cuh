@@ -149,11 +149,25 @@ __device__ __forceinline__ uint32_t bias_act_bf16x2(float a0, float a1, float b0
 // read and scattered partial-line writes when the row is hundreds of floats wide (embedding_dim 768).  Here the lane's
 // 16 finished values of a 32-row x 16-column half chunk go through the warp's 2 KB staging tile (64 B per row, 16-byte
 // chunk c of row r at c ^ ((r >> 1) & 3): conflict-free both ways) and come back as 8 rows x 64 contiguous bytes per
-// instruction; the residual is added on that side, read with the same coalesced pattern.
+// instruction; the residual is added on that side from values fetched with the same coalesced pattern (prefetch_resid_chunk).
 // ---------------------------------------------------------------------------------------------
+// The residual values of a 32 x 32 chunk in that coalesced mapping ([half][i]: row 8 i + lane / 4, columns 16 half + 4 (lane & 3)
+// .. + 3).  Issued right after the chunk's tcgen05.ld, BEFORE its wait, so that the global-load latency hides behind the
+// TMEM load and the activation arithmetic instead of sitting between the staging-tile read and the store.
+__device__ __forceinline__ void prefetch_resid_chunk(float4 (&rr)[2][4], const float* resid, int ldr, int lane, int row0, int M, int col0) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 8 * i + (lane >> 2);
+            rr[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (resid != nullptr && row < M)
+                rr[hh][i] = *reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * ldr + col0 + 16 * hh + 4 * (lane & 3));
+        }
+}
+
 __device__ __forceinline__ void store_f32_half_chunk_coalesced(uint32_t s_tile, const float (&y)[16], int lane, int row0, int M,
-                                                               float* __restrict__ out, int ldc, const float* __restrict__ resid,
-                                                               int ldr, int col0) {
+                                                               float* out, int ldc, const float4 (&rr4)[4], int col0) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const uint32_t dst = s_tile + static_cast<uint32_t>(lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
@@ -170,10 +184,7 @@ __device__ __forceinline__ void store_f32_half_chunk_coalesced(uint32_t s_tile, 
         const int row = row0 + r;
         if (row < M) {
             const int col = col0 + 4 * ch;
-            if (resid != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * ldr + col);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-            }
+            v.x += rr4[i].x; v.y += rr4[i].y; v.z += rr4[i].z; v.w += rr4[i].w;
             *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ldc + col) = v;
         }
     }

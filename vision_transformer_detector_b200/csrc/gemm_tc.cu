@@ -220,10 +220,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c0 = sub * 32; c0 < p.block_n; c0 += 128) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c0, v);
-                tmem_ld_wait();
-                const bool full = n0 + c0 + 32 <= p.N;      // block_n is a multiple of 32: chunks are never partial in the tile
+                const bool full = n0 + c0 + 32 <= p.N;
+                float4 rres[2][4];      // residual values of this chunk, fetched under the TMEM load (dead code for bf16 outputs)
+                const bool wide_f32 = OUT_F32 && full && p.N > 32 && p.ln_out == nullptr;
+                if (OUT_F32) { if (wide_f32) prefetch_resid_chunk(rres, p.resid, p.ldr, lane, m0 + quad * 32, p.M, n0 + c0); }
+                tmem_ld_wait();      // block_n is a multiple of 32: chunks are never partial in the tile
                 if (OUT_F32) {
-                    if (full && p.N > 32 && p.ln_out == nullptr) {
+                    if (wide_f32) {
                         // wide float32 output (embedding_dim > 32): finished values of the lane's row, 16 columns at a
                         // time, through the staging tile to coalesced stores (common.cuh); residual added on that side
                         const uint32_t s_tile = s_store0 + static_cast<uint32_t>(warp) * kStoreStride;
@@ -240,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 y16[4 * g + 3] = act_out<ACT, PRECISE>(__uint_as_float(v[16 * hh + 4 * g + 3]) + b4.w + pos_v);
                             }
                             store_f32_half_chunk_coalesced(s_tile, y16, lane, m0 + quad * 32, p.M, reinterpret_cast<float*>(p.out), p.ldc,
-                                                           p.resid, p.ldr, n0 + c0 + 16 * hh);
+                                                           rres[hh], n0 + c0 + 16 * hh);
                         }
                         continue;
                     }
