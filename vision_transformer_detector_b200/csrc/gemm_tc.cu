@@ -75,14 +75,16 @@ struct TcGemmArgs {
     int ln_ld;
 };
 
-// OUT: 0 bf16 (TMA store), 1 float32 (direct / coalesced stores, residual, fused LayerNorm), 2 split bf16 planes (hi, lo)
+// OUT: 0 bf16 (TMA store), 1 float32 rows of <= 32 columns (direct stores, residual, fused LayerNorm), 2 split bf16 planes (hi, lo),
+//      3 float32 rows wider than 32 columns (coalesced stores through the staging tile, residual prefetched)
 // PRECISE: exact activations (the fp32-accumulate mode)
 template <int ACT, int OUT, bool PRECISE>
 __global__ void __launch_bounds__(kThreads, 1)   // 96 registers is the most 576 threads can be granted (104 and 112 fail to launch)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmC_lo, const TcGemmArgs p) {
-    constexpr bool OUT_F32 = OUT == 1;
+    constexpr bool OUT_F32 = OUT == 1 || OUT == 3;
+    constexpr bool WIDE_F32 = OUT == 3;      // float32 rows wider than one 32-column chunk: coalesced stores through the staging tile
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_s;
@@ -222,8 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_32x32(t_row + c0, v);
                 const bool full = n0 + c0 + 32 <= p.N;
                 float4 rres[2][4];      // residual values of this chunk, fetched under the TMEM load (dead code for bf16 outputs)
-                const bool wide_f32 = OUT_F32 && full && p.N > 32 && p.ln_out == nullptr;
-                if (OUT_F32) { if (wide_f32) prefetch_resid_chunk(rres, p.resid, p.ldr, lane, m0 + quad * 32, p.M, n0 + c0); }
+                const bool wide_f32 = WIDE_F32 && full;
+                if constexpr (WIDE_F32) { if (wide_f32) prefetch_resid_chunk(rres, p.resid, p.ldr, lane, m0 + quad * 32, p.M, n0 + c0); }
                 tmem_ld_wait();      // block_n is a multiple of 32: chunks are never partial in the tile
                 if (OUT_F32) {
                     if (wide_f32) {
@@ -424,6 +426,8 @@ cudaError_t launch_variant(const TcGemmPlan& plan, const TcGemmArgs& a, cudaStre
 template <int ACT>
 cudaError_t launch_act(const TcGemmPlan& plan, const TcGemmArgs& a, cudaStream_t stream) {
     const GemmDesc& d = plan.desc;
+    if (d.out_f32 && d.N > 32 && !d.ln_out)      // wide float32 rows: separate instantiation, so that the narrow (28-wide) epilogue keeps its registers
+        return d.precise ? launch_variant<ACT, 3, true>(plan, a, stream) : launch_variant<ACT, 3, false>(plan, a, stream);
     if (d.out_f32) return d.precise ? launch_variant<ACT, 1, true>(plan, a, stream) : launch_variant<ACT, 1, false>(plan, a, stream);
     if (d.out_split) return launch_variant<ACT, 2, true>(plan, a, stream);      // split planes only exist in the fp32-accumulate mode
     return launch_variant<ACT, 0, false>(plan, a, stream);
@@ -501,9 +505,13 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     plan->n_tiles = n_tiles;
     plan->num_tiles = m_tiles * n_tiles;
     plan->grid = plan->num_tiles < num_sms ? plan->num_tiles : num_sms;
-    int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, d.K, d.lda, kBM);
+    // Inner tensor dimension rounded up to the 16-byte granule (columns [K, K8) are zero in A and in the packed weights by the
+    // contract above): with K = 28 the 56-byte rows put the out-of-bounds edge in the middle of a 16-byte chunk and the TMA
+    // unit takes a slow path — the 28 -> 960 layer ran 44.5 instead of 35.6 us (experiments/microbench/gemm_sweep.cu).
+    const int Kt = ((d.K + 7) / 8 * 8 <= d.lda && (d.K + 7) / 8 * 8 <= d.ldw) ? (d.K + 7) / 8 * 8 : d.K;
+    int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, Kt, d.lda, kBM);
     if (r) return r;
-    r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, d.K, d.ldw, bn);
+    r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, Kt, d.ldw, bn);
     if (r) return r;
     if (!d.out_f32) {
         // store map: columns [N, round_up(N, 8)) are part of the tensor and receive zeros
@@ -514,9 +522,9 @@ int tc_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     if (r) return r;
     plan->tmA_lo = plan->tmA; plan->tmB_lo = plan->tmB; plan->tmC_lo = plan->tmC;      // placeholders when unused
     if (d.split) {
-        r = make_tmap_bf16_2d(&plan->tmA_lo, d.A_lo, d.M, d.K, d.lda, kBM);
+        r = make_tmap_bf16_2d(&plan->tmA_lo, d.A_lo, d.M, Kt, d.lda, kBM);
         if (r) return r;
-        r = make_tmap_bf16_2d(&plan->tmB_lo, d.W_lo, d.N, d.K, d.ldw, bn);
+        r = make_tmap_bf16_2d(&plan->tmB_lo, d.W_lo, d.N, Kt, d.ldw, bn);
         if (r) return r;
     }
     if (d.out_split) r = make_tmap_bf16_2d_ex(&plan->tmC_lo, d.out_lo, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);

@@ -406,18 +406,22 @@ int tc2_gemm_make_plan(TcGemmPlan* plan, const GemmDesc& d, int num_sms) {
     plan->num_tiles = m_tiles * n_tiles;
     const int clusters = num_sms / 2;
     plan->grid = 2 * (plan->num_tiles < clusters ? plan->num_tiles : clusters);
-    int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, d.K, d.lda, kBM);
+    // Inner tensor dimension rounded up to the 16-byte granule (columns [K, K8) are zero in A and in the packed weights by the
+    // contract above): with K = 28 the 56-byte rows put the out-of-bounds edge in the middle of a 16-byte chunk and the TMA
+    // unit takes a slow path — the 28 -> 960 layer ran 44.5 instead of 35.6 us (experiments/microbench/gemm_sweep.cu).
+    const int Kt = ((d.K + 7) / 8 * 8 <= d.lda && (d.K + 7) / 8 * 8 <= d.ldw) ? (d.K + 7) / 8 * 8 : d.K;
+    int r = make_tmap_bf16_2d(&plan->tmA, d.A, d.M, Kt, d.lda, kBM);
     if (r) return r;
-    r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, d.K, d.ldw, bn / 2);
+    r = make_tmap_bf16_2d(&plan->tmB, d.W, d.N, Kt, d.ldw, bn / 2);
     if (r) return r;
     if (!d.out_f32) r = make_tmap_bf16_2d_ex(&plan->tmC, d.out, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
     else plan->tmC = plan->tmA;
     if (r) return r;
     plan->tmA_lo = plan->tmA; plan->tmB_lo = plan->tmB; plan->tmC_lo = plan->tmC;      // placeholders when unused
     if (d.split) {
-        r = make_tmap_bf16_2d(&plan->tmA_lo, d.A_lo, d.M, d.K, d.lda, kBM);
+        r = make_tmap_bf16_2d(&plan->tmA_lo, d.A_lo, d.M, Kt, d.lda, kBM);
         if (r) return r;
-        r = make_tmap_bf16_2d(&plan->tmB_lo, d.W_lo, d.N, d.K, d.ldw, bn / 2);
+        r = make_tmap_bf16_2d(&plan->tmB_lo, d.W_lo, d.N, Kt, d.ldw, bn / 2);
         if (r) return r;
     }
     if (d.out_split) r = make_tmap_bf16_2d_ex(&plan->tmC_lo, d.out_lo, d.M, (d.N + 7) / 8 * 8, d.ldc, 32, 32, 64);
