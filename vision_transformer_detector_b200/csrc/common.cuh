@@ -113,7 +113,11 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 // step): that epilogue is bound by instruction issue, not by the SFU, and the form costs 8 instead of 6.5 slots per element.
 // Also measured and dropped (r03, gpurun_out/r03a_ab.log): ONE reciprocal per pair, 1 / (q0 q1), and two multiplications
 // (1.5 SFU operations per element): 1.381 -> 1.341 ms per step on that layer although ncu has its XU pipe at 85 % — not worth
-// two more roundings in the activation.
+// two more roundings in the activation.  And (r03k_mish_poly_ab.log) one of four / one of two of the exponentials on the FMA pipe
+// (Cody-Waite + degree-5 polynomial, 2.1e-7, 11 issue slots): 1.382 -> 1.416 / 1.500 ms.  Every variant that adds instructions
+// to this epilogue loses, whatever it takes off the SFU: the four epilogue warps of a sub-partition are bound by their own
+// in-order instruction streams (ncu: 0.87 eligible warps per scheduler, stalls "wait" and "mio_throttle"), and 576 threads at
+// 96 registers are all the register file allows.
 __device__ __forceinline__ uint64_t mish2_fast(uint64_t x) {
     float t0, t1, n0, n1, q0, q1, r0, r1;
     f2_unpack(f2_mul(x, f2_pack(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
