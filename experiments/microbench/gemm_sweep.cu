@@ -39,6 +39,13 @@ int main() {
     void* ln = dalloc(size_t(Mmax) * 32 * 2, 0);
     float* g = (float*)dalloc(128, 0);
     std::vector<Case> cases;
+    // one tile per CTA or less: the latency of a launch (fill + drain), back to back with programmatic dependent launch
+    for (int M : {128, 148 * 128, 2 * 148 * 128, 4 * 148 * 128}) {
+        cases.push_back({"qkv 28->192 (1 n-tile)", M, 28, 192, 0, 0, 0, 0, 0, 192});
+        cases.push_back({"mlp_5 448->224 mish", M, 448, 224, 1, 0, 0, 0, 0, 0});
+        cases.push_back({"out 320->28 f32+res+ln", M, 320, 28, 0, 1, 1, 1, 0, 0});
+        cases.push_back({"mlp_4 896->448 mish pair", M, 896, 448, 1, 0, 0, 0, 1, 0});
+    }
     for (int M : {82944}) {
         cases.push_back({"qkv 28->960", M, 28, 960, 0, 0, 0, 0, 0, 0});
         cases.push_back({"mlp_1 28->3584 mish", M, 28, 3584, 1, 0, 0, 0, 0, 0});

@@ -59,7 +59,8 @@ typedef struct vitdet_config {
     int32_t patch_size;                /* default 17 */
     int32_t embedding_dim;             /* default 28 */
     int32_t num_heads;                 /* encoder_num_heads, default 8 */
-    int32_t key_dim;                   /* encoder_key_dim, default 40 (<= 64 in this build) */
+    int32_t key_dim;                   /* encoder_key_dim, default 40; <= 128 (heads wider than 64 run one attention CTA per SM,
+                                          and the fp32-accumulate mode takes its CUDA-core form for them) */
     int32_t mlp_quantities;            /* encoder_mlp_quantities, default 8 */
     int32_t repeat_times;              /* encoder_repeat_times, default 8 */
     int32_t head_last_units;           /* mlp_head_last_units, default 136 */

@@ -223,6 +223,20 @@ def test_attention_kernels_against_bf16_operands(B, T, H, d, kernel):
     assert np.sqrt(np.mean(err ** 2)) < 8e-4 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("B,T,H,d", [(2, 300, 3, 96), (1, 1296, 2, 128), (2, 65, 2, 72), (1, 129, 5, 104), (1, 1600, 2, 80)])
+def test_attention_wide_heads_against_bf16_operands(B, T, H, d):
+    """Heads wider than 64 (the reference accepts any key_dim): the kernel's two-box form — Q / K / V tiles of two 64-column
+    boxes, QK^T over up to eight k-steps, PV as two 64-column products, O in 128 TMEM columns, one CTA per SM."""
+    from vision_transformer_detector_b200 import ops
+    rng = np.random.default_rng(B * T + d)
+    q, k, v = (R(rng.normal(size=(B, T, H, d)) * 1.5) for _ in range(3))
+    ref = R(oracle.attention_core_bf16(q, k, v))
+    got = ops.attention(_t(q), _t(k), _t(v), mode="bf16").cpu().numpy()
+    err = np.abs(got - ref)
+    assert (err <= bf16_ulp(ref) + 2e-3 * np.abs(ref).max()).all(), float((err / np.abs(ref).max()).max())
+    assert np.sqrt(np.mean(err ** 2)) < 8e-4 * np.abs(ref).max()
+
+
 # ------------------------------------------------------------------------------------------------
 # whole model
 # ------------------------------------------------------------------------------------------------

@@ -68,6 +68,9 @@ def test_tiny_model_logits_match_oracle(mode, tol, use_mish):
          encoder_mlp_quantities=3, encoder_repeat_times=2),                       # ViT-B-like proportions, no padding
     dict(input_shape=(136, 68, 3), encoder_num_heads=3, encoder_key_dim=24, mlp_head_dense_mish_block_repeats=2),
     dict(encoder_mlp_quantities=1, encoder_repeat_times=1, mlp_head_dense_layers_quantity=1),
+    dict(encoder_num_heads=3, encoder_key_dim=96, encoder_repeat_times=2),       # heads wider than 64: two boxes per head tile
+    dict(input_shape=(136, 68, 3), encoder_num_heads=2, encoder_key_dim=128, encoder_repeat_times=1),
+    dict(encoder_num_heads=2, encoder_key_dim=72, encoder_repeat_times=1),
 ])
 def test_configuration_knobs(cfg_over):
     cfg = tiny_config(**cfg_over)

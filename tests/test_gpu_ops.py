@@ -87,7 +87,8 @@ def test_layernorm_matches_oracle(M, D):
 
 
 @pytest.mark.parametrize("mode,tol", [("bf16", TOL_BF16), ("fp32", TOL_FP32)])
-@pytest.mark.parametrize("B,T,H,d", [(2, 1296, 8, 40), (1, 4096, 2, 40), (2, 1600, 3, 64), (3, 100, 2, 40), (1, 64, 1, 8), (2, 65, 2, 24)])
+@pytest.mark.parametrize("B,T,H,d", [(2, 1296, 8, 40), (1, 4096, 2, 40), (2, 1600, 3, 64), (3, 100, 2, 40), (1, 64, 1, 8), (2, 65, 2, 24),
+                                     (2, 300, 3, 96), (1, 1296, 2, 128), (2, 65, 2, 72), (1, 129, 5, 104)])      # heads wider than 64: two boxes per head
 def test_attention_matches_oracle(B, T, H, d, mode, tol):
     from vision_transformer_detector_b200 import ops
     rng = np.random.default_rng(B * T + d)

@@ -79,10 +79,10 @@ attn_f32_kernel(const float* __restrict__ qkv, int ldq, float* __restrict__ ctx,
 }  // namespace
 
 // Tensor map over the fused qkv matrix [B*T, 3*H*hp] (bf16): boxes of 64 rows x 64 columns, 128B swizzle, placed at
-// column head * hp; hp = key_dim rounded up to 8.  For hp < 64 a box also carries the first columns of the next head
+// column head * hp (+ 64 for the second box of a head wider than 64); hp = key_dim rounded up to 8.  A box also carries the first columns of the next head
 // (zeros past the end of the matrix); the kernel neutralises them (attention_tc.cu).
 int attn_bf16_make_plan(AttnPlan* plan, const AttnDesc& d) {
-    if (d.d <= 0 || d.hp < d.d || d.hp > 64 || (d.hp % 8)) return -20;       // key_dim > 64 not supported in this build
+    if (d.d <= 0 || d.hp < d.d || d.hp > 128 || (d.hp % 8)) return -20;      // one or two 64-column boxes per head (key_dim <= 128)
     if ((d.ldq % 8) || (d.ldo % 8) || d.ldq < 3 * d.H * d.hp || d.ldo < d.H * d.hp) return -21;
     if ((reinterpret_cast<uintptr_t>(d.qkv) & 15) || (reinterpret_cast<uintptr_t>(d.ctx) & 15)) return -22;
     plan->desc = d;
@@ -100,7 +100,10 @@ cudaError_t attn_f32_launch(const AttnDesc& d, cudaStream_t stream) {
     switch ((d.d + 7) / 8 * 8) {   // pad columns of every head slot are zero in qkv
         VITDET_ATTN_F32(8) VITDET_ATTN_F32(16) VITDET_ATTN_F32(24) VITDET_ATTN_F32(32) VITDET_ATTN_F32(40)
         VITDET_ATTN_F32(48) VITDET_ATTN_F32(56) VITDET_ATTN_F32(64)
-        default: return cudaErrorInvalidValue;   // key_dim <= 64 in this build
+        // wider heads (the query and the accumulator no longer fit the register file: slow, but the exact form exists)
+        VITDET_ATTN_F32(72) VITDET_ATTN_F32(80) VITDET_ATTN_F32(88) VITDET_ATTN_F32(96) VITDET_ATTN_F32(104) VITDET_ATTN_F32(112)
+        VITDET_ATTN_F32(120) VITDET_ATTN_F32(128)
+        default: return cudaErrorInvalidValue;   // key_dim <= 128
     }
 #undef VITDET_ATTN_F32
     return cudaGetLastError();

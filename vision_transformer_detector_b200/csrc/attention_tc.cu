@@ -32,16 +32,22 @@ namespace {
 constexpr int kQ = 128;            // queries per CTA (UMMA M)
 constexpr int kKV = 128;           // keys per tile (UMMA N of QK^T, K of PV)
 constexpr int kHP = 64;            // head pitch in elements (one 128-byte swizzle row of bf16)
-constexpr int kStages = 3;
 constexpr int kThreads = 192;
 // softmax warps 0..3 (warp = TMEM lane quadrant); the TMA producer and the MMA issuer take the highest warp ids,
 // which the warp arbiter favours: the MMA issuer's wake-up latency is on the critical path of every tile
 constexpr int kProducerWarp = 4, kMmaWarp = 5;
-constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB
-constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one K tile or one V tile = two TMA boxes of 64 rows
+// NB = 64-column boxes per head tile: 1 for key_dim <= 64 (the product configuration: two CTAs per SM, three K/V stages),
+// 2 for 64 < key_dim <= 128 (one CTA per SM: O needs 128 TMEM columns and the tiles twice the shared memory).
+constexpr int kQBytes = kQ * kHP * 2;         // 16 KiB per 64-column box of Q
+constexpr int kTileBytes = kKV * kHP * 2;     // 16 KiB: one 64-column box of a K tile or a V tile = two TMA boxes of 64 rows
 constexpr int kBoxBytes = 64 * kHP * 2;
-constexpr int kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;   // S [0,128) f32 | P [128,192) bf16x2 | O [192,256) f32
+template <int NB> struct AttnCfg {
+    static constexpr int kStages = NB == 1 ? 3 : 2;
+    static constexpr int kTmemCols = NB == 1 ? 256 : 512;
+    static constexpr int kStageBytes = 2 * NB * kTileBytes;      // K boxes, then V boxes
+    static constexpr int kMinBlocks = NB == 1 ? 2 : 1;
+};
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;   // S [0,128) f32 | P [128,192) bf16x2 | O [192, 192 + 64 NB) f32
 constexpr float kRescaleThreshold = 8.f;      // log2 units: P stays <= 2^8 between rescales
 
 struct AttnTcArgs {
@@ -62,7 +68,7 @@ __device__ __forceinline__ float ex2f(float x) {
 // One key tile of the online softmax for the calling thread's query row: NCH = number of 32-key chunks that
 // hold at least one existing key (4 for a full tile), MASK = the last of them is partial.  Static loops only,
 // so that the 128 scores stay in registers.
-template <int NCH, bool MASK>
+template <int NCH, bool MASK, int NB>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t tO, uint32_t bar_s_free, uint32_t bar_pv_done,
                                              uint32_t bar_p_full, int lane, int j, int valid, float scale_log2,
                                              float& m_used, float& l) {
@@ -129,7 +135,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
         tc_fence_after();
         if (grow) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 2 * NB; ++c) {
                 uint32_t o[32];
                 tmem_ld_32x32(tO + 32u * c, o);
                 tmem_ld_wait();
@@ -152,8 +158,12 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tP, uint32_t 
     if (lane == 0) mbar_arrive(bar_p_full);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <int NB>
+__global__ void __launch_bounds__(kThreads, AttnCfg<NB>::kMinBlocks)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
+    constexpr int kStages = AttnCfg<NB>::kStages;
+    constexpr int kTmemCols = AttnCfg<NB>::kTmemCols;
+    constexpr int kStageBytes = AttnCfg<NB>::kStageBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kStages + 5];
     __shared__ uint32_t tmem_base_s;
@@ -170,7 +180,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
     const uint32_t base = smem_u32(smem_raw);
     if ((base & 1023u) != 0u) __trap();
     const uint32_t sQ = base;
-    const uint32_t sKV = base + kQBytes;               // stage s: K at + 2*s*tile, V right after
+    const uint32_t sKV = base + NB * kQBytes;          // stage s at + s * kStageBytes: NB boxes of K, then NB boxes of V
     const uint32_t bar_full = smem_u32(&bars[0]);
     const uint32_t bar_empty = smem_u32(&bars[kStages]);
     const uint32_t bar_q = smem_u32(&bars[2 * kStages]);
@@ -205,20 +215,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&tmQKV);
-            mbar_arrive_expect_tx(bar_q, kQBytes);
-            tma_load_2d(sQ, &tmQKV, bar_q, h * p.hp, row_base + q0);
-            tma_load_2d(sQ + kBoxBytes, &tmQKV, bar_q, h * p.hp, row_base + q0 + 64);
+            mbar_arrive_expect_tx(bar_q, NB * kQBytes);
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                tma_load_2d(sQ + nb * kQBytes, &tmQKV, bar_q, h * p.hp + 64 * nb, row_base + q0);
+                tma_load_2d(sQ + nb * kQBytes + kBoxBytes, &tmQKV, bar_q, h * p.hp + 64 * nb, row_base + q0 + 64);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < nkv; ++j) {
                 mbar_wait_relaxed(bar_empty + 8 * stage, phase ^ 1u);
-                mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kTileBytes);
-                const uint32_t dK = sKV + stage * 2 * kTileBytes;
+                mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+                const uint32_t dK = sKV + stage * kStageBytes, dV = dK + NB * kTileBytes;
                 const int r = row_base + j * kKV;
-                tma_load_2d(dK, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp, r);
-                tma_load_2d(dK + kBoxBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp, r + 64);
-                tma_load_2d(dK + kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp, r);
-                tma_load_2d(dK + kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp, r + 64);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    tma_load_2d(dK + nb * kTileBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp + 64 * nb, r);
+                    tma_load_2d(dK + nb * kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (p.H + h) * p.hp + 64 * nb, r + 64);
+                    tma_load_2d(dV + nb * kTileBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp + 64 * nb, r);
+                    tma_load_2d(dV + nb * kTileBytes + kBoxBytes, &tmQKV, bar_full + 8 * stage, (2 * p.H + h) * p.hp + 64 * nb, r + 64);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -232,17 +248,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         const uint32_t tS = tmem_base + kColS, tP = tmem_base + kColP, tO = tmem_base + kColO;
         const uint64_t dq = umma_desc_sw128_kmajor(sQ);
         const uint64_t dkv0 = umma_desc_sw128_kmajor(sKV);
-        constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4, kVOff = kTileBytes >> 4;     // descriptor address units (16 B)
+        constexpr uint32_t kStageStep = kStageBytes >> 4, kVOff = (NB * kTileBytes) >> 4, kBoxStep = kTileBytes >> 4;     // descriptor address units (16 B)
         mbar_wait(bar_q, 0);
         // Heads are stored hp (< 64) columns apart, so the 64-column TMA boxes also carry the first columns of the
         // next head.  In QK^T only the columns below 16 * k16 take part: clearing Q's columns [hp, 16 * k16) once makes
         // their products vanish whatever K holds there; V's extra columns only produce columns of O that are never
         // stored.  16-byte chunk c of row r sits at chunk c ^ (r & 7) of the 128-byte swizzled row.
         if (p.hp < 16 * p.k16) {
-            const int c_lo = p.hp >> 3, c_hi = 2 * p.k16;
+            const int c_lo = p.hp >> 3, c_hi = 2 * p.k16;      // 16-byte chunks of the head tile; chunk c lives in box c / 8
             for (int r = lane; r < kQ; r += 32)
                 for (int c = c_lo; c < c_hi; ++c)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + r * 128 + ((c ^ (r & 7)) << 4)), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sQ + (c >> 3) * kQBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4)), "r"(0u) : "memory");
             fence_proxy_async_smem();
             __syncwarp();
         }
@@ -260,6 +276,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                     if (p.k16 > 1) umma_bf16_ss(tS, dq + 2u, dk + 2u, idesc_qk, 1u);
                     if (p.k16 > 2) umma_bf16_ss(tS, dq + 4u, dk + 4u, idesc_qk, 1u);
                     if (p.k16 > 3) umma_bf16_ss(tS, dq + 6u, dk + 6u, idesc_qk, 1u);
+                    if (NB > 1) {       // head columns 64 .. 127: the second box of Q and of K
+                        for (int k = 4; k < p.k16; ++k)
+                            umma_bf16_ss(tS, dq + kBoxStep + 2u * (k - 4), dk + kBoxStep + 2u * (k - 4), idesc_qk, 1u);
+                    }
                     umma_commit(bar_s_full);
                 }
                 __syncwarp();
@@ -273,8 +293,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
                     const uint64_t dv = dkv0 + static_cast<uint64_t>(ps * kStageStep + kVOff);
                     // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
 #pragma unroll
-                    for (int k = 0; k < kKV / 16; ++k)
-                        umma_bf16_ts(tO, tP + 8u * k, dv + static_cast<uint64_t>(128u * k), idesc_pv, (k != 0) ? 1u : (j > 1 ? 1u : 0u));
+                    for (int nb = 0; nb < NB; ++nb)      // 64 output columns per V box
+#pragma unroll
+                        for (int k = 0; k < kKV / 16; ++k)
+                            umma_bf16_ts(tO + 64u * nb, tP + 8u * k, dv + static_cast<uint64_t>(nb * kBoxStep + 128u * k), idesc_pv,
+                                         (k != 0) ? 1u : (j > 1 ? 1u : 0u));
                     umma_commit(bar_empty + 8 * ps);
                     umma_commit(bar_pv_done);
                 }
@@ -295,7 +318,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
             mbar_wait(bar_s_full, j & 1);
             tc_fence_after();
 #define VITDET_TILE(NCH, MASK) \
-    softmax_tile<NCH, MASK>(tS, tP, tO, bar_s_free, bar_pv_done, bar_p_full, lane, j, valid, p.scale_log2, m_used, l)
+    softmax_tile<NCH, MASK, NB>(tS, tP, tO, bar_s_free, bar_pv_done, bar_p_full, lane, j, valid, p.scale_log2, m_used, l)
             if (valid == kKV) {
                 VITDET_TILE(4, false);
             } else {
@@ -319,7 +342,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs p) {
         const float inv = 1.f / l;
         __nv_bfloat16* orow = p.ctx + static_cast<size_t>(row_base + (q < p.T ? q : 0)) * p.ldo + h * p.hp;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2 * NB; ++c) {
             uint32_t o[32];
             tmem_ld_32x32(tO + 32u * c, o);
             tmem_ld_wait();
@@ -358,11 +381,18 @@ cudaError_t attn_tc_launch(const AttnPlan& plan, cudaStream_t stream) {
     a.hp = d.hp;
     a.k16 = (d.d + 15) / 16;
     a.scale_log2 = d.scale * 1.4426950408889634f;
-    const size_t smem = static_cast<size_t>(kQBytes) + static_cast<size_t>(kStages) * 2 * kTileBytes;
-    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc_kernel), static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
     dim3 grid((d.T + kQ - 1) / kQ, d.B * d.H);
-    return launch_kernel(attn_tc_kernel, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
+    if (d.hp <= 64) {
+        const size_t smem = static_cast<size_t>(kQBytes) + static_cast<size_t>(AttnCfg<1>::kStages) * AttnCfg<1>::kStageBytes;
+        cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc_kernel<1>), static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        return launch_kernel(attn_tc_kernel<1>, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
+    }
+    // 64 < key_dim <= 128: two 64-column boxes per head tile
+    const size_t smem = 2 * static_cast<size_t>(kQBytes) + static_cast<size_t>(AttnCfg<2>::kStages) * AttnCfg<2>::kStageBytes;
+    cudaError_t e = ensure_max_dynamic_smem(reinterpret_cast<const void*>(attn_tc_kernel<2>), static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    return launch_kernel(attn_tc_kernel<2>, grid, dim3(kThreads), smem, stream, 1, plan.tmQKV, a);
 }
 
 }  // namespace vitdet

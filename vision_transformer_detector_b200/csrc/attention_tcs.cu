@@ -365,6 +365,7 @@ attn_tcs_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 }  // namespace
 
 cudaError_t attn_tcs_launch(const AttnPlan& plan, const CUtensorMap& tm_lo, void* ctx_lo, cudaStream_t stream) {
+    if (plan.desc.hp > 64) return cudaErrorInvalidValue;      // hi and lo tiles: one 64-column box per head (wider heads: attention.cu)
     const AttnDesc& d = plan.desc;
     AttnTcsArgs a;
     a.ctx = static_cast<__nv_bfloat16*>(d.ctx);

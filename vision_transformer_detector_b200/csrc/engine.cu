@@ -57,7 +57,8 @@ int fail(int code, const char* fmt, ...) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-constexpr int kMaxKeyDim = 64;    // one 128-byte swizzle row of bf16 per head in shared memory
+constexpr int kMaxKeyDim = 128;   // one or two 64-column (128-byte swizzle row) boxes per head in shared memory
+constexpr int kMaxKeyDimSplit = 64;     // the split (fp32-accumulate) attention kernel keeps hi and lo tiles: one box per head
 // Elements per head in the qkv / ctx matrices: key_dim rounded up to 8 (16-byte rows for TMA and vector stores).  The
 // attention kernel's 64-column boxes start at column head * hp, so HBM carries no 64-wide pad (Q's spill columns are
 // cleared in shared memory, V's only produce output columns that are never stored).
@@ -1041,7 +1042,8 @@ static int forward_impl(vitdet_handle* h, const void* images, int B, int mode, f
     if (h->weights_dirty) { CU_TRY(cudaDeviceSynchronize()); h->weights_dirty = false; }
     const vitdet_config& c = h->cfg;
     const bool bf = mode == VITDET_MODE_BF16;
-    if (!bf && h->opt.fp32_tc) return forward_fp32_tc(h, images, B, logits, dpar, det, st, opts);
+    // fp32-accumulate mode on the tensor cores; heads wider than 64 take the IEEE CUDA-core form (the split attention kernel holds hi and lo tiles)
+    if (!bf && h->opt.fp32_tc && h->d <= kMaxKeyDimSplit) return forward_fp32_tc(h, images, B, logits, dpar, det, st, opts);
     RC_TRY(ensure_workspace(h, B, mode));
     const Dims m = dims_for(h, mode);
     const int T = h->T, L = c.repeat_times, q = c.mlp_quantities;
@@ -1792,7 +1794,7 @@ int vitdet_op_attention(const float* q, const float* k, const float* v, float* o
         { int dev2 = 0, sms2 = 148; CU_TRY(cudaGetDevice(&dev2)); CU_TRY(cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2));
           CU_TRY(attn_launch(env_options().attention, plan, sms2, st)); }
         unpack_ctx_kernel<__nv_bfloat16><<<blocks_for(rows * H * d), 256, 0, st>>>(ctx.as<__nv_bfloat16>(), rows, H, d, hp, out);
-    } else if (env_options().fp32_tc) {
+    } else if (env_options().fp32_tc && d <= kMaxKeyDimSplit) {
         // fp32-accumulate mode on the tensor cores: q | k | v as (hi, lo) planes, three-pass products (attention_tcs.cu)
         const int ld = 3 * H * hp;
         DevBuf planes, cplanes;
