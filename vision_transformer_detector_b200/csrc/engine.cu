@@ -597,6 +597,7 @@ static bool pair_kernel_legal(const GemmDesc& g) { return g.M >= 1024 && g.N >= 
 
 static bool use_pair_kernel(int pair_mode, const GemmDesc& g) {
     if (pair_mode == 0 || !pair_kernel_legal(g)) return false;
+    // (the head's M = 17 B rows on the single-CTA kernel instead: 0.239 vs 0.219 ms per step, profiles/r03m_ab.log)
     return pair_mode == 2 || g.K >= 512;
 }
 

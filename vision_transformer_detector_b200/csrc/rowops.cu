@@ -163,7 +163,7 @@ patchify_kernel(const IN* __restrict__ img, int H, int W, int p, int gh, int gw,
 // passes (CH float4 per lane), so x is read exactly once.
 // ------------------------------------------------------------------------------------------------
 template <int LPR, int CH, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CH <= 6 ? 4 : (CH <= 8 ? 3 : 2))      // rows of <= 768 floats: <= 64 registers, 32 resident warps per SM (was 24)
 layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int M, int D, float eps, T* __restrict__ y, int ldy) {
     constexpr int ROWS_PER_BLOCK = 256 / LPR;
@@ -505,6 +505,7 @@ cudaError_t ln_dispatch(const float* x, int ldx, const float* g, const float* b,
     if (chunks <= 1) return launch_kernel(layernorm_kernel<LPR, 1, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
     else if (chunks <= 2) return launch_kernel(layernorm_kernel<LPR, 2, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
     else if (chunks <= 4) return launch_kernel(layernorm_kernel<LPR, 4, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
+    else if (chunks <= 6) return launch_kernel(layernorm_kernel<LPR, 6, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
     else if (chunks <= 8) return launch_kernel(layernorm_kernel<LPR, 8, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
     else if (chunks <= 16) return launch_kernel(layernorm_kernel<LPR, 16, T>, dim3(grid), dim3(256), 0, st, 1, x, ldx, g, b, M, D, eps, y, ldy);
     return cudaErrorInvalidValue;   // embedding_dim > 2048 is outside what this build supports
