@@ -751,7 +751,11 @@ class VisionTransformerDetector:
 
     def collect(self, ticket: int) -> DetectionRecords:
         """Waits for a submit() ticket and returns its records as numpy arrays."""
-        B, packed, _ = self._inflight.pop(ticket)
+        entry = getattr(self, "_inflight", {}).pop(ticket, None)
+        if entry is None:
+            # not (or no longer) in flight: fail with the library's error type, like vitdet_collect itself does
+            raise _capi.VitdetError(_capi.E_INVALID, f"collect: ticket {ticket} is not in flight")
+        B, packed, _ = entry
         S = Constants.MAX_DETECT_OBJECTS_QUANTITY.value
         logits, dec, cid, cc, keep, cor = _alloc_records_np(B, S)
         pk = np.empty((B * S, 13), np.float32) if packed else None
