@@ -1,6 +1,7 @@
 """GPU parity tests, operator level: each CUDA kernel, called through the C ABI, against the oracle
 on the same seeded inputs.  Tolerances: north_star's 1e-3 (fp32 mode) and 2e-2 (bf16 mode),
 as max|gpu - ref| / max|ref| against the float64 oracle."""
+import os
 import numpy as np
 import pytest
 
@@ -119,3 +120,26 @@ def test_patchify_is_bit_exact(B, H, W, p):
     ref = oracle.extract_patches(img, p)
     got = ops.patchify(_t(img), p).cpu().numpy()
     assert np.array_equal(got, ref)
+
+
+def test_shared_memory_opt_in_grows_with_later_launches():
+    """A kernel whose dynamic shared-memory size depends on the model (the wide slot projection: 17 x D floats) must work
+    when a SMALL model runs first and a larger one later in the same process: the opt-in above 48 KB is remembered per
+    (kernel, device) with its size and raised on demand (launch.h).  Own process, so that no earlier test has set it."""
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch
+from vision_transformer_detector_b200 import ops
+rng = np.random.default_rng(0)
+for D in (64, 768, 1024):
+    x = rng.normal(size=(1, 40, D)).astype(np.float32)
+    w = (rng.normal(size=(D, 17)) / np.sqrt(D)).astype(np.float32)
+    b = rng.normal(size=(17,)).astype(np.float32)
+    ref = (x.astype(np.float64) @ w.astype(np.float64) + b).reshape(1, 17, 40)
+    got = ops.head_slots(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda(), mode="fp32").cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max(), D
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

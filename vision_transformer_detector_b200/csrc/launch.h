@@ -22,19 +22,20 @@ inline bool pdl_enabled() {
     return v == 1;
 }
 
-// Opt-in to more than 48 KB of dynamic shared memory, once per (kernel, device): the attribute is per device, and a
-// process may drive more than one.
+// Opt-in to more than 48 KB of dynamic shared memory, per (kernel, device): the attribute is per device, and a process may
+// drive more than one.  The configured size is remembered, and raised when a later launch of the same kernel needs more
+// (a kernel whose shared-memory size depends on the model, e.g. the wide slot projection, may first run on a small one).
 inline cudaError_t ensure_max_dynamic_smem(const void* kernel, int bytes) {
     static std::mutex mu;
-    static std::map<const void*, unsigned long long> done;      // kernel -> bitmask of devices already configured
+    static std::map<std::pair<const void*, int>, int> done;      // (kernel, device) -> bytes already configured
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lock(mu);
-    unsigned long long& mask = done[kernel];
-    if (dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+    int& have = done[std::make_pair(kernel, dev)];
+    if (have >= bytes) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess && dev < 64) mask |= 1ull << dev;
+    if (e == cudaSuccess) have = bytes;
     return e;
 }
 
