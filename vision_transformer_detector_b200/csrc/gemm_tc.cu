@@ -209,11 +209,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // Bias is read straight from global memory below (a warp-wide broadcast that stays in L1): no staging
             // barrier per tile, so the sixteen epilogue warps drift apart and their SFU phases interleave.
             const float* bs = p.bias + n0;      // valid for columns < N only; the tail path guards its reads
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-
             const int row = m0 + quad * 32 + lane;
             const bool row_ok = row < p.M;
+            // Narrow float32 rows (the 28-wide residual stream: output projection): the thread's residual row is fetched
+            // BEFORE the wait for the accumulator, so that the global-load latency hides behind the tile's MMAs.
+            float4 rpre[8];
+            bool rpre_ok = false;
+            if constexpr (OUT == 1) {
+                if (p.resid != nullptr && p.block_n <= 32 && sub == 0 && row_ok) {
+                    const float* rr = p.resid + static_cast<size_t>(row) * p.ldr + n0;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) rpre[g] = (n0 + 4 * g < p.n_store) ? *reinterpret_cast<const float4*>(rr + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rpre_ok = true;
+                }
+            }
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
             float pos_v = 0.f;
             if (p.pos != nullptr && row_ok) pos_v = __ldg(p.pos + (row % p.pos_period));
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -270,7 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             x[0] = __uint_as_float(v[4 * g + 0]) + b4.x; x[1] = __uint_as_float(v[4 * g + 1]) + b4.y;
                             x[2] = __uint_as_float(v[4 * g + 2]) + b4.z; x[3] = __uint_as_float(v[4 * g + 3]) + b4.w;
                             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
+                            if (OUT == 1 && rpre_ok) r4 = rpre[g];
+                            else if (rrow) r4 = *reinterpret_cast<const float4*>(rrow + n);
                             const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
