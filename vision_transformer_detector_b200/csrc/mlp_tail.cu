@@ -144,6 +144,14 @@ mlp_tail_kernel(const __grid_constant__ TailMaps maps, const TailArgs p) {
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ph ^= 1u) {
             const int row = tile * kTM + r;
+            // the residual row of the last layer is fetched NOW (the warps that will need it), so that its global-load latency
+            // hides behind the three MMA -> epilogue stages of the tile instead of sitting in the last one
+            float4 xpre[8];
+            if (half == 0 && row < p.M) {
+                const float* xrow_pre = p.x + static_cast<size_t>(row) * p.ldx;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) xpre[g] = (4 * g < p.ldx) ? *reinterpret_cast<const float4*>(xrow_pre + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             // ---- layers 0 and 1: activations -> shared memory (A operand of the next layer) ----
             for (int l = 0; l < 2; ++l) {
                 mbar_wait(bar_d + 8 * l, ph);
@@ -207,7 +215,7 @@ mlp_tail_kernel(const __grid_constant__ TailMaps maps, const TailArgs p) {
                         const int n = 4 * g;
                         float h4[4] = {0.f, 0.f, 0.f, 0.f};
                         if (n < p.ldx) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(xrow + n);
+                            const float4 r4 = xpre[g];
                             const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
