@@ -126,3 +126,20 @@ def test_category_names_match_the_reference_table():
     import csv
     rows = list(csv.DictReader(open(path)))
     assert [r["name"] for r in sorted(rows, key=lambda r: float(r["id_in_model"]))] == list(vd.COCO_CATEGORY_NAMES)
+
+
+def test_traffic_capture_is_stamped_for_the_current_kernel_sources():
+    """bench.py quotes roofline.traffic from profiles/gemm_mlp_2_traffic.json only while the capture's stamp equals the hash
+    of the dominant kernel's sources (gemm_tc2.cu + the headers it includes + the nvcc flags).  A change to those files
+    needs a new `ncu --set full` capture (scripts/gpu_round2.sh + scripts/summarize_profiles.py), otherwise the bench line
+    silently carries `traffic: null`."""
+    import json
+    import os
+    from vision_transformer_detector_b200 import build
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "gemm_mlp_2_traffic.json")
+    t = json.load(open(path))
+    assert t["kernel_hash"] == build.kernel_hash(), "re-capture the dominant GEMM under ncu: its sources changed"
+    assert t["rows_per_launch"] == 64 * 1296
+    # no re-reads: measured DRAM traffic within 5 % of the algorithmic bytes 2 (M (K + N) + K N)
+    algorithmic = 2.0 * (82944 * (3584 + 1792) + 3584 * 1792)
+    assert 0.9 * algorithmic < t["traffic_bytes_per_launch"] < 1.05 * algorithmic
