@@ -17,6 +17,10 @@
 //               TMEM) when it grew by more than 2^8, so most tiles skip the correction.
 // TMEM columns: S [0,128) f32 | P [128,192) bf16x2 | O [192,256) f32.
 //
+// Heads wider than 64 (64 < key_dim <= 128; the reference accepts any key_dim) run the same kernel with NB = 2: every Q / K /
+// V tile is two 64-column boxes, QK^T walks up to eight k-steps across them, PV is issued once per box of V into O
+// [192, 320), the CTA allocates 512 TMEM columns and the SM holds one CTA with two K/V stages.
+//
 // The binding unit is the SFU, not the tensor pipe: per 128 x 128 score tile the CTA needs 16 384 ex2 at
 // 16/clk/SM = 1024 clk, against ~450 clk of MMA at head_dim 40.  Tiles of 128 keys (not 64)
 // because the per-tile fixed costs (barrier round trips, TMEM load/store latency) are what keeps the
